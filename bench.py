@@ -1,0 +1,376 @@
+#!/usr/bin/env python3
+"""
+bench.py -- headline benchmark of the ASW hot path (BASELINE.json metric: Mpix*disparities/s, ASW 35x35).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[1] -- KITTI-size 1242x375 synthetic rectified pair
+(simplestereo_b200.synth.synth_pair, seed 0), 128 disparities (0..127), StereoASW winSize=35 gammaC=5 gammaP=17.5.
+A "step" is one full disparity map of that pair.
+
+  value   Mpix*disp/s = W*H*D / t, inputs already resident in HBM, device-timed (CUDA events per step on the
+          launching stream, L2 flushed between steps, max over ranks).
+  e2e     the same metric through the public API StereoASW.compute(left, right): pinned HOST numpy arrays in,
+          host int16 map out, H2D + kernels + D2H inside the timed region.
+  roofline  the aggregation kernel against the MEASURED FP32 FFMA peak of this GPU (the path is FP32-issue bound,
+          SURVEY.md 8d), with achieved HBM GB/s against MEASURED_PEAKS.json beside it.
+  cpu_baseline  the unmodified reference (oracle/_ref) timed on this box's host cores on a bounded full-width
+          crop and extrapolated by exact window-element counts (N=1, rank 0 only).
+
+At N > 1 the frame is sharded into N image-row stripes (one rank per GPU) and reassembled with one NCCL
+all-gather (strong scaling: total work fixed).
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, else the C port) on the same config.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, MAXD, MIND, WIN, GC, GP = 1242, 375, 127, 0, 35, 5.0, 17.5
+D = MAXD - MIND + 1
+METRIC = "Mpix*disparities/s (ASW 35x35)"
+UNIT = "Mpix*disp/s"
+WORKLOAD = "KITTI-size 1242x375 synthetic rectified pair, 128 disp (0..127), StereoASW winSize=35 gammaC=5 gammaP=17.5"
+
+
+def mpixdisp(seconds):
+    return W * H * D / seconds / 1e6
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU reference arm
+# ----------------------------------------------------------------------------------------------------
+
+def window_elements(width, height, win, min_d, max_d):
+    """Exact number of (x, d, i, j) window elements the reference evaluates in its left pass
+    (_passive.cpp:56-84): rows ii in-image, right column jj >= 0, left column kk < W."""
+    p = win // 2
+    y = np.arange(height)
+    nrows = np.minimum(y, p) + 1 + np.minimum(height - 1 - y, p)          # in-image window rows per output row
+    total_cols = 0
+    x = np.arange(width)
+    for d in range(min_d, max_d + 1):
+        xs = x[x >= d]
+        if xs.size == 0:
+            break
+        lo = np.maximum(0, p - (xs - d))            # first j with jj = x-d-p+j >= 0
+        hi = np.minimum(win - 1, width - 1 - xs + p)  # last j with kk = x-p+j <= W-1
+        total_cols += int(np.maximum(hi - lo + 1, 0).sum())
+    return int(nrows.sum()) * total_cols
+
+
+def cpu_reference_sample(target_s, crop_rows=None):
+    """Time the reference on a full-width crop taken from the middle of the C2 pair and extrapolate to the
+    full frame by exact element counts.  Returns (Mpix*disp/s full-frame equivalent, info dict)."""
+    import oracle
+    from simplestereo_b200.synth import synth_pair
+    left, right, _ = synth_pair(W, H, MAXD, 0)
+    cores = len(os.sched_getaffinity(0))
+    use_ref = oracle.ref_available()
+    if crop_rows is None:
+        # survey anchor: 18.5 ns per window element per core for the unmodified reference
+        ns_per_el = 18.5 if use_ref else 1.0
+        per_row = window_elements(W, 1, WIN, MIND, MAXD) * ns_per_el * 1e-9 / max(cores, 1)   # one window row
+        crop_rows = cores
+        while crop_rows + cores <= H and window_rows(crop_rows + cores) * per_row <= target_s:
+            crop_rows += cores
+    y0 = (H - crop_rows) // 2
+    lc = np.ascontiguousarray(left[y0:y0 + crop_rows])
+    rc = np.ascontiguousarray(right[y0:y0 + crop_rows])
+    if use_ref:
+        _, dt = oracle.ref_asw(lc, rc, WIN, MAXD, MIND, GC, GP, False, with_time=True, timeout=1800)
+        kind = "reference"
+    else:
+        oracle.build(ref=False)
+        t0 = time.perf_counter()
+        oracle.asw(lc, rc, WIN, MAXD, MIND, GC, GP, False)
+        dt = time.perf_counter() - t0
+        kind = "port"
+    scale = window_elements(W, H, WIN, MIND, MAXD) / window_elements(W, crop_rows, WIN, MIND, MAXD)
+    t_full = dt * scale
+    info = {"kind": kind, "cores": cores, "crop_rows": crop_rows,
+            "sample": f"full-width {W}x{crop_rows} crop of the workload pair ({dt:.2f} s measured), extrapolated x{scale:.2f} "
+                      f"to {W}x{H} by exact window-element counts"}
+    return mpixdisp(t_full), info, t_full
+
+
+def window_rows(h):
+    p = WIN // 2
+    y = np.arange(h)
+    return int((np.minimum(y, p) + 1 + np.minimum(h - 1 - y, p)).sum())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    total = max(args.steps + args.warmup, 1)
+    target = min(30.0, max(2.0, 150.0 / total))
+    vals, times = [], []
+    info = None
+    rows = None
+    for k in range(args.warmup + args.steps):
+        v, info, t_full = cpu_reference_sample(target, rows)
+        rows = info["crop_rows"]
+        if k >= args.warmup:
+            vals.append(v)
+            times.append(t_full)
+    value = statistics.median(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": statistics.median(times) * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "ms_per_step is the full-frame time extrapolated from the bounded sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, **info},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import simplestereo_b200 as ss
+    from simplestereo_b200 import _cabi
+    from simplestereo_b200.sharding import ShardedStereoASW
+    from simplestereo_b200.synth import synth_pair
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (simplestereo_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L = _cabi.lib()
+    _cabi.check(L.ss_init(local))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    left, right, _ = synth_pair(W, H, MAXD, 0)
+    matcher = ss.passive.StereoASW(WIN, MAXD, MIND, GC, GP, consistent=False)
+    sharded = ShardedStereoASW(matcher, mode="rows") if world > 1 else None
+
+    # pinned host staging for the end-to-end leg
+    h_left = torch.from_numpy(left).pin_memory()
+    h_right = torch.from_numpy(right).pin_memory()
+    d_left = h_left.to(dev)
+    d_right = h_right.to(dev)
+    d_out = torch.empty((H, W), dtype=torch.int16, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        if world > 1:
+            return sharded.compute_device(d_left, d_right)
+        _cabi.check(L.ss_asw_compute_device(d_left.data_ptr(), d_right.data_ptr(), W, H, WIN, MAXD, MIND, GC, GP, 0, 0, H,
+                                            d_out.data_ptr(), stream.cuda_stream))
+        return d_out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        step_device()
+    barrier()
+
+    # ---- device-timed leg -------------------------------------------------------------------------
+    L.ss_profile_reset()
+    L.ss_profile_enable(1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(0)                        # L2 flush between timed iterations (not timed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        result = step_device()
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    agg_ms, agg_launches, total_launches = _cabi.profile_read()
+    L.ss_profile_enable(0)
+    ms_per_step = total_ms / args.steps
+    value = mpixdisp(ms_per_step * 1e-3)
+
+    # ---- end-to-end leg: public API, pinned host buffers in, host map out ---------------------------
+    np_left, np_right = h_left.numpy(), h_right.numpy()
+
+    def step_e2e():
+        if world > 1:
+            dl = h_left.to(dev, non_blocking=True)
+            dr = h_right.to(dev, non_blocking=True)
+            return sharded.compute_device(dl, dr).cpu()
+        return matcher.compute(np_left, np_right)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_host = step_e2e()
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+
+    # sanity: device leg and e2e leg produce the same map
+    same = bool(np.array_equal(np.asarray(out_host), result.cpu().numpy()[:H]))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the aggregation kernel -------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    fp32_peak = _cabi.measure_fp32_peak(stream.cuda_stream)
+    rows_per_rank = -(-H // world)
+    flops_per_launch = 4.0 * W * rows_per_rank * D * WIN * WIN          # 4 flop per nominal window element
+    bytes_per_launch = 8.0 * W * rows_per_rank                          # compulsory HBM bytes: 2*3 in + 2 out per pixel
+    agg_avg_s = (agg_ms / max(agg_launches, 1)) * 1e-3
+    achieved_tf = flops_per_launch / agg_avg_s / 1e12
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = prof.get("k_aggregate_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {
+        "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
+        "traffic": traffic,
+        "kernel": "k_aggregate<ASW,128>", "kernel_ms": agg_avg_s * 1e3, "kernel_share_of_step": agg_ms / total_ms if world == 1 else None,
+        "peak_source": "FFMA-only microbenchmark run live on this GPU (ss_measure_fp32_peak); nominal 74.4 TFLOP/s",
+        "algorithmic_flops_per_launch": flops_per_launch,
+        "hbm": {"achieved": bytes_per_launch / agg_avg_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": bytes_per_launch / agg_avg_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch},
+    }
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, info, _ = cpu_reference_sample(15.0)
+            cpu = {"value": v, "unit": UNIT, **info}
+        except Exception as ex:  # the GPU numbers stand on their own
+            cpu = {"value": None, "unit": UNIT, "error": repr(ex)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sharding": "none" if world == 1 else f"{world} image-row stripes + one NCCL all_gather",
+                   "l2": "flushed between timed steps (256 MiB fill)", "timing": "CUDA events per step on the launching stream, max over ranks",
+                   "maps_equal_across_legs": same},
+        "clocks": clocks,
+        "e2e": {"value": mpixdisp(e2e_s), "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": 2 * W * H * 3, "d2h_bytes_per_step": W * H * 2},
+        "gpu_launches": int(total_launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "wall_s_timed_region": t_wall,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

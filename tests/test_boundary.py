@@ -1,0 +1,77 @@
+"""CPU-side tests of the drop-in boundary: the C-ABI library loads and exports every declared symbol,
+the Python mirror validates like the reference, and nothing silently falls back to the CPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import simplestereo_b200 as ss
+from simplestereo_b200 import _cabi
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_header_symbols_are_exported():
+    hdr = open(os.path.join(ROOT, "include", "ss_passive.h")).read()
+    declared = set(re.findall(r"\b(ss_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for s in declared:
+        assert hasattr(lib, s), f"{s} not exported by libsspassive.so"
+    assert _cabi.lib().ss_abi_version() == 1
+
+
+def test_library_is_sm100a_and_uses_tma_and_packed_fp32():
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    elf = subprocess.run(["cuobjdump", "-lelf", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf
+    sass = subprocess.run(["cuobjdump", "-sass", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass          # cp.async.bulk (TMA) staging of window rows
+    assert "FFMA2" in sass           # packed fp32 accumulation
+
+
+def test_python_side_validation_without_gpu():
+    a = np.zeros((8, 9, 3), np.uint8)
+    with pytest.raises(ValueError, match="winSize must be a positive odd number!"):
+        ss.passive.StereoASW(winSize=4)
+    with pytest.raises(ValueError, match="winSize must be a positive odd number!"):
+        ss.passive.StereoGSW(winSize=0)
+    with pytest.raises(TypeError, match="Wrong type input!"):
+        ss.passive.StereoASW().compute(a.astype(np.float32), a)
+    with pytest.raises(ValueError, match="Wrong image dimensions!"):
+        ss.passive.StereoGSW().compute(a, a[:4])
+    with pytest.raises(ValueError, match="Invalid input format!"):
+        ss.passive.StereoASW().compute([1, 2], a)
+    m = ss.passive.StereoASW()
+    assert (m.winSize, m.maxDisparity, m.minDisparity, m.gammaC, m.gammaP, m.consistent) == (35, 16, 0, 5, 17.5, False)
+    g = ss.passive.StereoGSW()
+    assert (g.winSize, g.maxDisparity, g.minDisparity, g.gamma, g.fMax, g.iterations, g.bins) == (11, 16, 0, 10, 120, 3, 20)
+
+
+@pytest.mark.skipif(_cuda(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback():
+    a = np.zeros((8, 9, 3), np.uint8)
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        ss.passive.StereoASW(winSize=3, maxDisparity=2).compute(a, a)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "simplestereo_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh", ".cpp")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f

@@ -1,0 +1,232 @@
+"""
+GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the public Python API,
+i.e. through the C ABI of libsspassive.so; the oracle is only the checker.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import simplestereo_b200 as ss
+from simplestereo_b200.synth import synth_pair
+from tests import parity
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+
+GOLD = cases.load_golden()
+TIE_STRESS = {"asw_const", "asw_const_consistent", "gsw_const"}
+
+
+def test_library_is_the_cuda_one():
+    from simplestereo_b200 import _cabi
+    assert os.path.exists(_cabi.LIB_PATH)
+    assert _cabi.lib().ss_init(0) == 0
+
+
+def test_tsukuba_known_answer_image():
+    """The reference's own golden image (examples/res/tsukuba/disparityASW.png), via examples/010:44-45."""
+    import cv2
+    l, r = cases.load_inputs(("tsukuba", None))
+    d = ss.passive.StereoASW(35, 16, 0, 17.5, 17.5, False).compute(l, r)
+    assert d.dtype == np.int16 and d.shape == l.shape[:2]
+    img = cv2.applyColorMap(cv2.normalize(d, None, 0, 255, cv2.NORM_MINMAX, dtype=cv2.CV_8UC1), cv2.COLORMAP_JET)
+    kat = cv2.imread(os.path.join(cases.HERE, "disparityASW.png"))
+    nbad = int((img != kat).any(axis=2).sum())
+    if nbad:
+        # any differing pixel must be a float32 near-tie of the float64 reference costs
+        ref = oracle.asw(l, r, 35, 16, 0, 17.5, 17.5, False, stages=True, cost=True)
+        parity.adjudicate_left(d, GOLD["asw_tsukuba_kat"], ref["cost"], 0)
+    assert nbad <= 0.001 * d.size
+
+
+@pytest.mark.parametrize("name,spec,kw", cases.ASW_CASES, ids=[c[0] for c in cases.ASW_CASES])
+def test_asw_golden_cases(name, spec, kw):
+    l, r = cases.load_inputs(spec)
+    m = ss.passive.StereoASW(**kw)
+    out = m.compute(l, r)
+    ref = oracle.asw(l, r, stages=True, cost=True, **kw)
+    assert np.array_equal(ref["final"], GOLD[name]) or name not in GOLD       # oracle == reference (pinned on CPU too)
+    gpu = m.compute_staged(l, r, cost=True)
+    assert np.array_equal(gpu["final"], out)
+    parity.check_cost(gpu["cost"], ref["cost"].astype(np.float64))
+    frac = None if name in TIE_STRESS else parity.MAX_MISMATCH_FRACTION
+    nl, nr = parity.check_staged(gpu, ref, ref["cost"], ref["cost"], kw["minDisparity"], kw["consistent"], frac)
+    if nl == 0 and nr == 0:
+        assert np.array_equal(out, GOLD[name])
+
+
+@pytest.mark.parametrize("name,spec,kw", cases.GSW_CASES, ids=[c[0] for c in cases.GSW_CASES])
+def test_gsw_golden_cases(name, spec, kw):
+    l, r = cases.load_inputs(spec)
+    m = ss.passive.StereoGSW(**kw)
+    out = m.compute(l, r)
+    ref = oracle.gsw(l, r, stages=True, cost=True, **kw)
+    gpu = m.compute_staged(l, r, cost=True)
+    assert np.array_equal(gpu["final"], out)
+    parity.check_cost(gpu["cost_left"], ref["cost_left"], "cost_left")
+    parity.check_cost(gpu["cost_right"], ref["cost_right"], "cost_right")
+    frac = None if name in TIE_STRESS else parity.MAX_MISMATCH_FRACTION
+    nl, nr = parity.check_staged(gpu, ref, ref["cost_left"], ref["cost_right"], kw["minDisparity"], True, frac, saturation=None)
+    if nl == 0 and nr == 0:
+        assert np.array_equal(out, GOLD[name])
+
+
+def test_saturated_noise_pair_only_flips_near_ties():
+    """i.i.d. noise saturates the truncated AD: every argmin is a rounding tie."""
+    l, r = cases.load_inputs(("noise", (96, 24, 5)))
+    kw = dict(winSize=15, maxDisparity=20, minDisparity=0, gammaC=5, gammaP=17.5, consistent=True)
+    gpu = ss.passive.StereoASW(**kw).compute_staged(l, r, cost=True)
+    ref = oracle.asw(l, r, stages=True, cost=True, **kw)
+    parity.check_cost(gpu["cost"], ref["cost"])
+    parity.check_staged(gpu, ref, ref["cost"], ref["cost"], 0, True, max_fraction=None)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_randomised_small_shapes(seed):
+    rng = np.random.default_rng(1000 + seed)
+    for _ in range(6):
+        w, h = int(rng.integers(1, 150)), int(rng.integers(1, 40))
+        mind = int(rng.integers(0, 5))
+        maxd = mind + int(rng.integers(0, 70))
+        win = int(rng.choice([1, 3, 7, 11, 21, 35]))
+        cons = bool(rng.integers(0, 2))
+        l, r, _ = synth_pair(w, h, maxd, int(rng.integers(0, 1 << 30)))
+        kw = dict(winSize=win, maxDisparity=maxd, minDisparity=mind, gammaC=float(rng.uniform(3, 20)), gammaP=float(rng.uniform(5, 30)), consistent=cons)
+        gpu = ss.passive.StereoASW(**kw).compute_staged(l, r, cost=True)
+        ref = oracle.asw(l, r, stages=True, cost=True, **kw)
+        parity.check_cost(gpu["cost"], ref["cost"])
+        parity.check_staged(gpu, ref, ref["cost"], ref["cost"], mind, cons, max_fraction=0.01)
+        wing = int(rng.choice([1, 3, 5, 9]))
+        kwg = dict(winSize=wing, maxDisparity=maxd, minDisparity=mind, gamma=int(rng.integers(3, 20)), fMax=float(rng.uniform(30, 200)), iterations=int(rng.integers(0, 4)), bins=20)
+        gpu = ss.passive.StereoGSW(**kwg).compute_staged(l, r, cost=True)
+        ref = oracle.gsw(l, r, stages=True, cost=True, **kwg)
+        parity.check_cost(gpu["cost_left"], ref["cost_left"], "cost_left")
+        parity.check_cost(gpu["cost_right"], ref["cost_right"], "cost_right")
+        parity.check_staged(gpu, ref, ref["cost_left"], ref["cost_right"], mind, True, max_fraction=0.01, saturation=None)
+
+
+def test_multi_chunk_disparity_range():
+    """D = 300 -> three 128-wide chunks merged through the atomicMin keys."""
+    l, r, _ = synth_pair(400, 12, 299, 9)
+    kw = dict(winSize=9, maxDisparity=299, minDisparity=0, gammaC=5, gammaP=17.5, consistent=True)
+    gpu = ss.passive.StereoASW(**kw).compute_staged(l, r, cost=True)
+    ref = oracle.asw(l, r, stages=True, cost=True, **kw)
+    parity.check_cost(gpu["cost"], ref["cost"])
+    parity.check_staged(gpu, ref, ref["cost"], ref["cost"], 0, True)
+
+
+# ---- BASELINE.json full-size configurations: oracle on a stripe + size-independent properties -----
+
+C2 = dict(winSize=35, maxDisparity=127, minDisparity=0, gammaC=5, gammaP=17.5)
+
+
+@pytest.fixture(scope="module")
+def c2_pair():
+    return synth_pair(1242, 375, 127, 0)
+
+
+@pytest.fixture(scope="module")
+def c2_full(c2_pair):
+    l, r, _ = c2_pair
+    return ss.passive.StereoASW(consistent=True, **C2).compute_staged(l, r)
+
+
+def test_c2_stripe_against_oracle(c2_pair, c2_full):
+    l, r, _ = c2_pair
+    rows = (180, 192)
+    ref = oracle.asw(l, r, consistent=True, stages=True, cost=True, rows=rows, **C2)
+    sl = slice(*rows)
+    g = {k: c2_full[k][sl] for k in ("left", "right", "invalid", "final")}
+    rr = {k: ref[k][sl] for k in ("left", "right", "invalid", "final")}
+    parity.check_staged(g, rr, ref["cost"], ref["cost"], 0, True)
+
+
+def test_c2_row_stripes_equal_full_frame(c2_pair, c2_full):
+    """Row-stripe sharding (the multi-GPU unit) is bit-identical to the full-frame call."""
+    l, r, _ = c2_pair
+    m = ss.passive.StereoASW(consistent=True, **C2)
+    for r0, r1 in ((0, 47), (47, 94), (300, 375), (187, 188)):
+        assert np.array_equal(m.compute(l, r, rows=(r0, r1)), c2_full["final"][r0:r1])
+
+
+def test_c2_recovers_ground_truth(c2_pair, c2_full):
+    _, _, gt = c2_pair
+    left = c2_full["left"]
+    assert (left == gt).mean() > 0.85          # reference: 91.8 % on this pair
+    assert left.min() >= 0 and left.max() <= 127
+    assert (c2_full["final"] >= 0).all()
+
+
+def test_identical_pair_gives_min_disparity():
+    """cost(d=minD) is exactly 0 when left == right shifted by minD... here minD = 0: every pixel -> 0."""
+    l, _, _ = synth_pair(1242, 64, 127, 4)
+    d = ss.passive.StereoASW(consistent=True, **C2).compute(l, l.copy())
+    assert (d == 0).all()
+    g = ss.passive.StereoGSW(winSize=35, maxDisparity=127, minDisparity=0).compute(l, l.copy())
+    assert (g == 0).all()
+
+
+def test_c3_gsw_stripe_against_oracle(c2_pair):
+    l, r, _ = c2_pair
+    kw = dict(winSize=35, maxDisparity=127, minDisparity=0, gamma=10, fMax=120, iterations=3, bins=20)
+    rows = (100, 104)
+    gpu = ss.passive.StereoGSW(**kw).compute_staged(l, r)
+    ref = oracle.gsw(l, r, stages=True, cost=True, rows=rows, **kw)
+    sl = slice(*rows)
+    g = {k: gpu[k][sl] for k in ("left", "right", "invalid", "final")}
+    rr = {k: ref[k][sl] for k in ("left", "right", "invalid", "final")}
+    parity.check_staged(g, rr, ref["cost_left"], ref["cost_right"], 0, True, saturation=None)
+
+
+def test_c4_shape_win51_d256_stripe():
+    """Middlebury-full parameters (win 51, 256 disparities, L-R) on a full-width band."""
+    l, r, _ = synth_pair(2880, 72, 255, 2)
+    kw = dict(winSize=51, maxDisparity=255, minDisparity=0, gammaC=5, gammaP=17.5, consistent=True)
+    gpu = ss.passive.StereoASW(**kw).compute_staged(l, r)
+    rows = (34, 37)
+    ref = oracle.asw(l, r, stages=True, cost=True, rows=rows, **kw)
+    sl = slice(*rows)
+    g = {k: gpu[k][sl] for k in ("left", "right", "invalid", "final")}
+    rr = {k: ref[k][sl] for k in ("left", "right", "invalid", "final")}
+    parity.check_staged(g, rr, ref["cost"], ref["cost"], 0, True)
+
+
+# ---- API / validation behaviour ------------------------------------------------------
+
+def test_error_behaviour_matches_reference():
+    a = np.zeros((8, 9, 3), np.uint8)
+    with pytest.raises(ValueError, match="winSize must be a positive odd number!"):
+        ss.passive.StereoASW(winSize=4)
+    with pytest.raises(TypeError, match="Wrong type input!"):
+        ss.passive.StereoASW().compute(a.astype(np.float32), a)
+    with pytest.raises(TypeError, match="Wrong type input!"):
+        ss.passive.StereoASW().compute(a, a.astype(np.float32))
+    with pytest.raises(ValueError, match="Wrong image dimensions!"):
+        ss.passive.StereoASW().compute(a[:, :, 0], a[:, :, 0])
+    with pytest.raises(ValueError, match="Wrong image dimensions!"):
+        ss.passive.StereoASW().compute(a, a[:, :8])
+    with pytest.raises(ValueError, match="Invalid input format!"):
+        ss.passive.StereoASW().compute(a.tolist(), a)
+    with pytest.raises(ValueError, match="Invalid input format!"):
+        ss.passive.StereoGSW(gamma=10.5).compute(a, a)
+    with pytest.raises(ValueError):
+        ss.passive.StereoASW(gammaC=0).compute(a, a)
+    with pytest.raises(ValueError):
+        ss.passive.StereoASW(minDisparity=-1).compute(a, a)
+    m = ss.passive.StereoASW(winSize=3, maxDisparity=2)
+    m.winSize = 4                                       # bypass the constructor check, hit the C-side one
+    with pytest.raises(ValueError, match="winSize must be a positive odd number!"):
+        m.compute(a, a)
+
+
+def test_non_contiguous_input_is_accepted():
+    l, r, _ = synth_pair(64, 20, 8, 1)
+    m = ss.passive.StereoASW(winSize=7, maxDisparity=8)
+    want = m.compute(l, r)
+    lf, rf = np.asfortranarray(l), np.asfortranarray(r)
+    assert np.array_equal(m.compute(lf, rf), want)
+    big_l = np.zeros((20, 128, 3), np.uint8); big_l[:, ::2] = l
+    big_r = np.zeros((20, 128, 3), np.uint8); big_r[:, ::2] = r
+    assert np.array_equal(m.compute(big_l[:, ::2], big_r[:, ::2]), want)
