@@ -258,10 +258,13 @@ __device__ __forceinline__ float support_weight(const float4 c, const float4 n, 
 
 template <int V> struct IC { static constexpr int value = V; };
 
+// A warp covers 4 x-groups (of 8 columns) x 8 disparity groups (of 4): shared-memory loads are deduplicated
+// per warp instruction, so this shape minimises distinct bytes per step (W1 128 B, W2 3 x 224 B, E 512 B =
+// 12 wavefronts, against 18 for a 1 x 32 arrangement; measured with tools/microbench2.cu).
 template <int DC> struct AggCfg {
-    static constexpr int NDG = DC / 4;          // disparity groups (of 4) per warp
-    static constexpr int XGW = 32 / NDG;        // x groups (of 8) per warp
-    static constexpr int NW = TILE_X / (8 * XGW);
+    static constexpr int ND = DC / 4;           // disparity groups (of 4) in the chunk
+    static constexpr int NDB = ND / 8;          // blocks of 8 disparity groups
+    static constexpr int NW = 2 * NDB;          // warps: 2 x-group blocks (of 4) x NDB
     static constexpr int NT = NW * 32;
     static constexpr int NRp = TILE_X + DC;
 #ifdef SS_MINB1
@@ -368,8 +371,8 @@ __global__ void __launch_bounds__(AggCfg<DC>::NT, AggCfg<DC>::MINB) k_aggregate(
     }
 
     // lane -> register tile: 8 consecutive x, 4 consecutive disparities
-    const int dg = lane % C::NDG, xgw = lane / C::NDG;
-    const int xb = 8 * (warp * C::XGW + xgw);              // tile-relative first column
+    const int dg = (warp % C::NDB) * 8 + (lane & 7);
+    const int xb = 8 * ((warp / C::NDB) * 4 + (lane >> 3)); // tile-relative first column
     const int kb = 4 * dg;                                 // chunk-relative first disparity
     const int R0 = T - 8 - xb + kb;                        // first reversed right-centre index (multiple of 4)
 
@@ -379,10 +382,6 @@ __global__ void __launch_bounds__(AggCfg<DC>::NT, AggCfg<DC>::MINB) k_aggregate(
 #pragma unroll
         for (int b = 0; b < 2; ++b) { acc0[a][b] = 0ull; acc1[a][b] = 0ull; }
 
-    // phase-A mapping: a thread owns one column of a 32-column block and every JS-th window offset
-    constexpr int JS = NT / 32;
-    const int jq = warp;                                   // == tid >> 5
-
     for (int n = 0; n < nsteps; ++n) {
         const int i = i_lo + n;
         if (tid == 0 && n + 1 < nsteps) issue_F(n + 1);
@@ -390,49 +389,52 @@ __global__ void __launch_bounds__(AggCfg<DC>::NT, AggCfg<DC>::MINB) k_aggregate(
         mbar_wait((n & 1) ? barF1 : barF0, (n >> 1) & 1);
 
         // ---- phase A: tabulate the two support-weight rows of window row i -------------------
+        // A warp owns a 32-column block (right-image blocks first, then left-image blocks) and walks all
+        // window offsets j in batches of 4: loads first, stores last, so the four exp/sqrt chains overlap
+        // (smem stores between them would otherwise serialise the loads of the next weight).
         {
             const float4 *f1 = F1s + (n & 1) * NU;
             const float4 *f2 = F2s + (n & 1) * NV;
             const float *parg = reinterpret_cast<const float *>(PAs + (n & 1) * winq);
-            // right: W2s[j][r], r reversed (xr = xr_max - r): centre NR-1-r, neighbour NR-1-r+j
+            constexpr int NCBR = NRp / 32, NCB = NCBR + T / 32;
 #pragma unroll 1
-            for (int cb = 0; cb < NRp / 32; ++cb) {
-                const int r = cb * 32 + lane;
-                float *dst = W2s + r;
-                if (r < NR) {
-                    const float4 c = C2s[NR - 1 - r];
-                    const float4 *nb = f2 + (NR - 1 - r);
-#pragma unroll 2
-                    for (int j = jq; j < win; j += JS) {
-                        float w = support_weight<GSW>(c, nb[j], P.kC, GSW ? 0.f : parg[j]);
-                        if (GSW && P.iterations <= 0) w = ((i == pad) && (j == pad)) ? 1.f : 0.f;
-                        dst[j * NRp] = w;
-                    }
-                } else {
-                    for (int j = jq; j < win; j += JS) dst[j * NRp] = 0.f;
-                }
-            }
-            // left: W1s[j][x], centre (y, x0+x), neighbour (ii, x0+x-pad+j)
-#pragma unroll 1
-            for (int cb = 0; cb < T / 32; ++cb) {
-                const int x = cb * 32 + lane;
-                const float4 c = C1s[x];
-                const float4 *nb = f1 + x;
-                float *dst = W1s + x;
+            for (int cb = warp; cb < NCB; cb += C::NW) {
+                const bool right = cb < NCBR;                 // warp-uniform
+                const int col = (right ? cb : cb - NCBR) * 32 + lane;
+                // right: W2s[j][r], r reversed (xr = xr_max - r): centre NR-1-r, neighbour NR-1-r+j
+                // left : W1s[j][x], centre (y, x0+x), neighbour (ii, x0+x-pad+j)
+                const bool live = !right || col < NR;
+                const int src = right ? (live ? NR - 1 - col : 0) : col;
+                const float4 c = right ? C2s[src] : C1s[src];
+                const float4 *nb = (right ? f2 : f1) + src;
+                float *dst = (right ? W2s : W1s) + col;
+                const int pitch = right ? NRp : T;
                 // right-border abort of the LEFT pass of GSW only (_passive.cpp:445-446, :470-471)
-                const bool quirk = GSW && (x0 + x + pad >= g.W);
-#pragma unroll 2
-                for (int j = jq; j < win; j += JS) {
-                    float w = support_weight<GSW>(c, nb[j], P.kC, GSW ? 0.f : parg[j]);
-                    if (GSW) {
-                        const bool centre = (i == pad) && (j == pad);
-                        if (P.iterations <= 0) w = centre ? 1.f : 0.f;
-                        else if (quirk) {
-                            const bool keep = (y == 0) ? (i == pad) : centre;
-                            if (!keep) w = 0.f;
+                const bool quirk = GSW && !right && (x0 + col + pad >= g.W);
+#pragma unroll 1
+                for (int j0 = 0; j0 < win; j0 += 4) {
+                    float pa[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (!GSW) {
+                        const float4 t = *reinterpret_cast<const float4 *>(parg + j0);
+                        pa[0] = t.x; pa[1] = t.y; pa[2] = t.z; pa[3] = t.w;
+                    }
+                    float w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = min(j0 + u, win - 1);
+                        w[u] = support_weight<GSW>(c, nb[j], P.kC, pa[u]);
+                        if (GSW) {
+                            const bool centre = (i == pad) && (j == pad);
+                            if (P.iterations <= 0) w[u] = centre ? 1.f : 0.f;
+                            else if (quirk) {
+                                const bool keep = (y == 0) ? (i == pad) : centre;
+                                if (!keep) w[u] = 0.f;
+                            }
                         }
                     }
-                    dst[j * T] = w;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (j0 + u < win) dst[(j0 + u) * pitch] = live ? w[u] : 0.f;
                 }
             }
         }
@@ -544,11 +546,11 @@ __global__ void __launch_bounds__(AggCfg<DC>::NT, AggCfg<DC>::MINB) k_aggregate(
             }
         }
 #pragma unroll
-        for (int off = 1; off < C::NDG; off <<= 1) {
+        for (int off = 1; off < 8; off <<= 1) {       // the 8 disparity groups of this warp share lane bits 0-2
             const u64 o = __shfl_xor_sync(0xffffffffu, best, off);
             best = o < best ? o : best;
         }
-        if (dg == 0 && x < g.W && best != KEY_NONE) atomicMin(P.bestL + (size_t)rowo * g.W + x, best);
+        if ((lane & 7) == 0 && x < g.W && best != KEY_NONE) atomicMin(P.bestL + (size_t)rowo * g.W + x, best);
         if (x < g.W) {
             const size_t o = ((size_t)rowo * g.W + x) * P.Dp + (size_t)ch * DC + kb;
             if (P.vol0) *reinterpret_cast<float4 *>(P.vol0 + o) = make_float4(out0[0], out0[1], out0[2], out0[3]);
