@@ -45,7 +45,8 @@ def gather_rows(stripe, height, group=None):
     n = dist.get_world_size(group)
     s, w = stripe.shape
     full = torch.empty((n * s, w), dtype=stripe.dtype, device=stripe.device)
-    dist.all_gather_into_tensor(full, stripe.contiguous(), group=group)
+    # int16 is not a collective dtype (neither NCCL nor gloo): gather the raw bytes
+    dist.all_gather_into_tensor(full.view(torch.uint8), stripe.contiguous().view(torch.uint8), group=group)
     return full[:height]
 
 
@@ -93,7 +94,8 @@ class ShardedStereoASW:
             if self.world == 1:
                 return stripe[:h]
             full = self._buf("full", (self.world * s, w), torch.int16, dev)
-            dist.all_gather_into_tensor(full, stripe, group=self.group)
+            # int16 is not an NCCL dtype: gather the raw bytes
+            dist.all_gather_into_tensor(full.view(torch.uint8), stripe.view(torch.uint8), group=self.group)
             return full[:h]
         # disparity-range shards: keys planes [left | right] per rank
         d0, d1 = disparity_shards(mind, maxd, self.world)[self.rank]
@@ -103,10 +105,11 @@ class ShardedStereoASW:
         _cabi.check(L.ss_asw_partial_device(d_img1.data_ptr(), d_img2.data_ptr(), w, h, win, maxd, mind, gc, gp, cons,
                                             0, h, d0, d1, mine[0].data_ptr(), mine[1].data_ptr() if cons else None, st))
         if self.world > 1:
-            allk = self._buf("allkeys", (self.world, planes, npx), torch.int64, dev)
+            # rank-major concatenation along dim 0 (the layout every backend's all_gather_into_tensor accepts)
+            allk = self._buf("allkeys", (self.world * planes, npx), torch.int64, dev)
             dist.all_gather_into_tensor(allk, mine, group=self.group)
             _cabi.check(L.ss_merge_keys_device(allk.data_ptr(), self.world, planes * npx, st))
-            merged = allk[0]
+            merged = allk[:planes]
         else:
             merged = mine
         out = self._buf("out", (h, w), torch.int16, dev)

@@ -230,3 +230,48 @@ def test_non_contiguous_input_is_accepted():
     big_l = np.zeros((20, 128, 3), np.uint8); big_l[:, ::2] = l
     big_r = np.zeros((20, 128, 3), np.uint8); big_r[:, ::2] = r
     assert np.array_equal(m.compute(big_l[:, ::2], big_r[:, ::2]), want)
+
+
+# ---- sharding entry points (single GPU emulating N shards; the N-rank path is tests/test_sharding.py + bench.py) ----
+
+def test_disparity_range_shards_merge_equals_unsharded():
+    """ss_asw_partial_device over 4 disparity shards + ss_merge_keys_device + ss_finalize_keys_device
+    == the unsharded call (config C5's partition, on one GPU)."""
+    import torch
+    from simplestereo_b200 import _cabi
+    from simplestereo_b200.sharding import disparity_shards
+    l, r, _ = synth_pair(320, 40, 150, 6)
+    h, w = l.shape[:2]
+    kw = dict(winSize=21, maxDisparity=150, minDisparity=3, gammaC=5, gammaP=17.5, consistent=True)
+    want = ss.passive.StereoASW(**kw).compute(l, r)
+    L = _cabi.lib()
+    dl, dr = torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()
+    n = 4
+    keys = torch.empty((n * 2, h * w), dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for k, (d0, d1) in enumerate(disparity_shards(3, 150, n)):
+        _cabi.check(L.ss_asw_partial_device(dl.data_ptr(), dr.data_ptr(), w, h, 21, 150, 3, 5.0, 17.5, 1, 0, h, d0, d1,
+                                            keys[2 * k].data_ptr(), keys[2 * k + 1].data_ptr(), st))
+    _cabi.check(L.ss_merge_keys_device(keys.data_ptr(), n, 2 * h * w, st))
+    out = torch.empty((h, w), dtype=torch.int16, device="cuda")
+    _cabi.check(L.ss_finalize_keys_device(keys[0].data_ptr(), keys[1].data_ptr(), w, h, 3, out.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_row_stripes_device_entry_point():
+    import torch
+    from simplestereo_b200 import _cabi
+    from simplestereo_b200.sharding import row_stripes
+    l, r, _ = synth_pair(200, 37, 30, 8)
+    h, w = l.shape[:2]
+    m = ss.passive.StereoGSW(winSize=9, maxDisparity=30)
+    want = m.compute(l, r)
+    L = _cabi.lib()
+    dl, dr = torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    got = torch.zeros((h, w), dtype=torch.int16, device="cuda")
+    for r0, r1 in row_stripes(h, 3):
+        _cabi.check(L.ss_gsw_compute_device(dl.data_ptr(), dr.data_ptr(), w, h, *m._args(), r0, r1, got[r0:r1].data_ptr(), st))
+    torch.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy(), want)
