@@ -32,6 +32,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -45,7 +46,8 @@ namespace {
 
 typedef unsigned long long u64;
 
-constexpr int TILE_X = 64;          // output columns per block
+constexpr int TILE_X = 64;          // output columns per block of k_aggregate (GSW)
+constexpr int TILE_WS = 96;         // output columns per block of k_aggregate_ws (ASW)
 constexpr float SENTINEL = 1.0e18f; // feature value of out-of-image pixels
 constexpr u64 KEY_NONE = ~0ull;
 
@@ -128,11 +130,13 @@ struct Geom {
     int DC, nch;       // disparity chunk, number of chunks covering [dLo, dHi]
     int row0, row1;    // output rows [row0,row1)
     int erow0, erow1;  // input rows needed [erow0,erow1) = output rows +- pad, clipped
-    int ntx;           // number of 64-column tiles
+    int T;             // output columns per block: 64 (k_aggregate, GSW) or 96 (k_aggregate_ws, ASW)
+    int EP;            // ASW: bytes per cost-volume column (DC + 4: the +4 skews columns 8 apart onto different banks)
+    int ntx;           // number of T-column tiles
     int UW;            // padded row pitch of the left feature image and of the cost volume (u' = u + pad)
     int VW, PL2;       // padded row pitch / left padding of the right feature image (xr' = xr + PL2)
-    int NU;            // cost-volume columns per tile  = TILE_X + win - 1
-    int NR, NRp;       // right centres per tile = TILE_X + DC - 1, padded pitch TILE_X + DC
+    int NU;            // cost-volume columns per tile  = T + win - 1
+    int NR, NRp;       // right centres per tile = T + DC - 1, padded pitch T + DC
     int NV;            // right feature columns per tile = NR + win - 1
 };
 
@@ -190,7 +194,7 @@ __global__ void k_prep_features(const uint8_t *__restrict__ img, float4 *__restr
 
 template <bool GSW>
 __global__ void k_cost_volume(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img2,
-                              float *__restrict__ E, Geom g, float f_max) {
+                              void *__restrict__ Eout, Geom g, float f_max) {
     const int k4 = g.DC / 4;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;   // over UW * DC/4
     if (t >= g.UW * k4) return;
@@ -198,6 +202,7 @@ __global__ void k_cost_volume(const uint8_t *__restrict__ img1, const uint8_t *_
     const int r = blockIdx.y, ch = blockIdx.z;
     const int y = g.erow0 + r, u = up - g.pad;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
+    int vi[4] = {0, 0, 0, 0};
     if (u >= 0 && u < g.W) {
         const uint8_t *p = img1 + 3 * ((size_t)y * g.W + u);
         const int b1 = p[0], g1 = p[1], r1 = p[2];
@@ -213,13 +218,19 @@ __global__ void k_cost_volume(const uint8_t *__restrict__ img1, const uint8_t *_
                     const float e = __fsqrt_rn((float)(db * db + dg * dg + dr * dr));
                     v[q] = fminf(f_max, e);
                 } else {
-                    v[q] = (float)min(40, abs(db) + abs(dg) + abs(dr));   // _passive.cpp:77-79
+                    vi[q] = min(40, abs(db) + abs(dg) + abs(dr));            // _passive.cpp:77-79
                 }
             }
         }
     }
-    float4 *dst = reinterpret_cast<float4 *>(E + (((size_t)ch * (g.erow1 - g.erow0) + r) * g.UW + up) * g.DC + kq);
-    *dst = make_float4(v[0], v[1], v[2], v[3]);
+    const size_t col = ((size_t)ch * (g.erow1 - g.erow0) + r) * g.UW + up;
+    if (GSW) {
+        *reinterpret_cast<float4 *>(static_cast<float *>(Eout) + col * g.DC + kq) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+        // ASW: the truncated AD is an integer in [0,40] -> one byte; 4 disparities per 32-bit word
+        *reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(Eout) + col * g.EP + kq) =
+            (uint32_t)vi[0] | ((uint32_t)vi[1] << 8) | ((uint32_t)vi[2] << 16) | ((uint32_t)vi[3] << 24);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -230,7 +241,7 @@ struct AggParams {
     Geom g;
     const float4 *F1;     // left features  [erows][UW]
     const float4 *F2;     // right features [erows][VW]
-    const float *E;       // raw cost volume [nch][erows][UW][DC]
+    const void *E;        // raw cost volume: GSW float [nch][erows][UW][DC]; ASW uint8 [nch][erows][UW][EP]
     const float *proxarg; // ASW: -log2(e)*r/gammaP per window offset [win][(win+3)&~3]
     float kC;             // ASW: -log2(e)/gammaC ; GSW: (float)gamma
     int iterations;       // GSW only (<=0: centre weight only)
@@ -238,6 +249,7 @@ struct AggParams {
     float *vol0;          // optional: ASW cost / GSW right cost  [(rows)*W*Dp]
     float *vol1;          // optional: GSW left cost
     int Dp;               // pitch of vol0/vol1 (= nch*DC)
+    int freerun;          // timing experiment (SS_FREERUN=1): consumers ignore the barriers, producers idle; results are garbage
 #ifdef SS_DEBUG_DUMP
     float *dbg;           // [0]=bx [1]=by [2]=step ; dump of W1s, W2s, Es of that block/step follows at dbg+16
 #endif
@@ -359,7 +371,8 @@ __global__ void __launch_bounds__(AggCfg<DC>::NT, AggCfg<DC>::MINB) k_aggregate(
         const int ii = y - pad + i_lo + n;
         const uint32_t bytes = (uint32_t)(NU * DC * 4);
         mbar_expect_tx(barE, bytes);
-        tma_load_1d(smem_u32(Es), P.E + ((size_t)ch * erows + (ii - g.erow0)) * e_plane + (size_t)x0 * DC, bytes, barE);
+        tma_load_1d(smem_u32(Es), static_cast<const float *>(P.E) + ((size_t)ch * erows + (ii - g.erow0)) * e_plane + (size_t)x0 * DC,
+                    bytes, barE);
     };
 
     if (tid == 0) {
@@ -560,6 +573,370 @@ __global__ void __launch_bounds__(AggCfg<DC>::NT, AggCfg<DC>::MINB) k_aggregate(
 }
 
 // ------------------------------------------------------------------------------------------
+// k_aggregate_ws -- warp-specialised ASW aggregation (the headline kernel)
+//
+// One block = (output row y, 96 columns, one chunk of DC disparities).  Consumer warps (3 column blocks x DC/32
+// disparity blocks, each warp 4 x-groups x 8 disparity groups, lane tile 8 columns x 4 disparities) only run
+// the packed-FP32 accumulation; producer warps tabulate the support-weight rows of the NEXT window row into the
+// other half of a double buffer and drive the TMA copies.  mbarrier full/empty pairs order the three streams
+// (features -> producers, weights -> consumers, raw costs -> consumers), so the FP32 pipe never waits for the
+// exp/sqrt chains the way the single-role k_aggregate does.  Raw costs are bytes (0..40), 4 disparities per
+// 32-bit shared load, converted with I2F.U8 on the otherwise idle XU pipe.
+// At DC=128 the block is 16 warps, one block per SM: producers drop to 56 registers and consumers grow to 152
+// (setmaxnreg), which removes the spills of the 128-register version.
+// ------------------------------------------------------------------------------------------
+
+template <int DC> struct WsCfg {
+    static constexpr int T = TILE_WS;
+    static constexpr int NDB = DC / 32;          // blocks of 32 disparities (8 groups of 4)
+    static constexpr int CW = 3 * NDB;           // consumer warps
+    static constexpr int PW = NDB;               // producer warps
+    static constexpr int NT = (CW + PW) * 32;    // 512 / 256 / 128 threads
+    static constexpr int MINB = 4 / NDB;         // 1 / 2 / 4 blocks per SM
+    static constexpr int NRp = T + DC;
+    static constexpr int EP = DC + 4;            // bytes per raw-cost column
+};
+
+struct WsSmem {         // stage s of a double-buffered region lives at base + s * size
+    int e, f1, f2, pa, c1, c2, w1, w2, bars, total;
+    int ebytes, f1bytes, f2bytes, pabytes, w1bytes, w2bytes;
+};
+__host__ __device__ inline WsSmem ws_smem(int win, int DC) {
+    const int T = TILE_WS, NU = T + win - 1, NR = T + DC - 1, NRp = T + DC, NV = NR + win - 1, EP = DC + 4;
+    const int winq = (win + 3) >> 2;
+    WsSmem p;
+    int off = 0;
+    p.ebytes = (NU * EP + 15) & ~15;
+    p.f1bytes = NU * 16;
+    p.f2bytes = NV * 16;
+    p.pabytes = winq * 16;
+    p.w1bytes = (win * T * 4 + 15) & ~15;
+    p.w2bytes = (win * NRp * 4 + 15) & ~15;
+    p.e = off;  off += 2 * p.ebytes;
+    p.f1 = off; off += 2 * p.f1bytes;
+    p.f2 = off; off += 2 * p.f2bytes;
+    p.pa = off; off += 2 * p.pabytes;
+    p.c1 = off; off += T * 16;
+    p.c2 = off; off += NRp * 16;
+    p.w1 = off; off += 2 * p.w1bytes;
+    p.w2 = off; off += 2 * p.w2bytes;
+    p.bars = off; off += 16 * 8;
+    p.total = off;
+    return p;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float u8_to_f32(uint32_t w, int byte) {
+    float f;
+    // one I2F.U8 with a byte selector
+    asm("cvt.rn.f32.u8 %0, %1;" : "=f"(f) : "r"((w >> (8 * byte)) & 0xffu));
+    return f;
+}
+
+template <int DC, int REM>
+__global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws(const AggParams P) {
+    typedef WsCfg<DC> C;
+    constexpr int T = C::T, NRp = C::NRp, EP = C::EP, CW = C::CW, PW = C::PW;
+    extern __shared__ __align__(128) unsigned char smem[];
+
+    const Geom &g = P.g;
+    const int win = g.win, pad = g.pad;
+    const int NU = g.NU, NR = g.NR, NV = g.NV;
+    const WsSmem sp = ws_smem(win, DC);
+    const int winq = (win + 3) >> 2, winp = winq * 4;
+    const uint32_t bar0 = smem_u32(smem + sp.bars);
+    // barrier slots: 0 centres | 1,2 fullF | 3,4 emptyF | 5,6 fullW | 7,8 emptyW | 9,10 fullE | 11,12 emptyE
+    auto BAR = [&](int slot) { return bar0 + 8u * (uint32_t)slot; };
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * T;
+    const int y = g.row0 + blockIdx.y;
+    const int ch = blockIdx.z;
+    const int dlo = g.dLo + ch * DC;
+    const int erows = g.erow1 - g.erow0;
+    const int i_lo = max(0, pad - y), i_hi = min(win - 1, g.H - 1 - y + pad);
+    const int nsteps = i_hi - i_lo + 1;
+
+    if (tid == 0) {
+        mbar_init(BAR(0), 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(BAR(1 + s), 1);
+            mbar_init(BAR(3 + s), PW);
+            mbar_init(BAR(5 + s), PW);
+            mbar_init(BAR(7 + s), CW);
+            mbar_init(BAR(9 + s), 1);
+            mbar_init(BAR(11 + s), CW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= CW) {
+        // =================================== producers ===================================
+        if (DC == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (P.freerun) return;
+        const int pw = warp - CW;
+        const int f2_start = x0 - dlo - DC + 1 - pad + g.PL2;
+        const int c2_start = x0 - dlo - DC + 1 + g.PL2;
+        const size_t e_plane = (size_t)g.UW * EP;
+        const float4 *C1s = reinterpret_cast<const float4 *>(smem + sp.c1);
+        const float4 *C2s = reinterpret_cast<const float4 *>(smem + sp.c2);
+
+        auto issue_F = [&](int n) {
+            const int i = i_lo + n, ii = y - pad + i, st = n & 1;
+            const uint32_t bar = BAR(1 + st);
+            mbar_expect_tx(bar, (uint32_t)((NU + NV + winq) * 16));
+            tma_load_1d(smem_u32(smem + (sp.f1 + st * sp.f1bytes)), P.F1 + (size_t)(ii - g.erow0) * g.UW + x0, NU * 16, bar);
+            tma_load_1d(smem_u32(smem + (sp.f2 + st * sp.f2bytes)), P.F2 + (size_t)(ii - g.erow0) * g.VW + f2_start, NV * 16, bar);
+            tma_load_1d(smem_u32(smem + (sp.pa + st * sp.pabytes)), P.proxarg + (size_t)i * winp, winq * 16, bar);
+        };
+        auto issue_E = [&](int n) {
+            const int ii = y - pad + i_lo + n, st = n & 1;
+            const uint32_t bar = BAR(9 + st);
+            mbar_expect_tx(bar, (uint32_t)sp.ebytes);
+            tma_load_1d(smem_u32(smem + (sp.e + st * sp.ebytes)),
+                        static_cast<const uint8_t *>(P.E) + ((size_t)ch * erows + (ii - g.erow0)) * e_plane + (size_t)x0 * EP,
+                        (uint32_t)sp.ebytes, bar);
+        };
+
+        if (pw == 0 && lane == 0) {
+            mbar_expect_tx(BAR(0), (uint32_t)((T + NR) * 16));
+            tma_load_1d(smem_u32(smem + sp.c1), P.F1 + (size_t)(y - g.erow0) * g.UW + x0 + pad, T * 16, BAR(0));
+            tma_load_1d(smem_u32(smem + sp.c2), P.F2 + (size_t)(y - g.erow0) * g.VW + c2_start, NR * 16, BAR(0));
+            issue_F(0);
+        }
+        constexpr int NCBR = NRp / 32, NCB = NCBR + T / 32;   // 32-column blocks: right image first, then left
+        const int NB = winq;                                 // batches of 4 window offsets
+        const int npairs = NCB * NB;                         // (column block, batch) pairs, split evenly over the producers
+        const int p_begin = (pw * npairs) / PW, p_end = ((pw + 1) * npairs) / PW;
+        const int cb_begin = p_begin / NB, jb_begin = p_begin - cb_begin * NB;
+        // plain ints: keep the shared-memory plan out of local memory
+        const int o_f1 = sp.f1, o_f2 = sp.f2, o_pa = sp.pa, o_w1 = sp.w1, o_w2 = sp.w2;
+        const int b_f1 = sp.f1bytes, b_f2 = sp.f2bytes, b_pa = sp.pabytes, b_w1 = sp.w1bytes, b_w2 = sp.w2bytes;
+
+        for (int n = 0; n < nsteps; ++n) {
+            const int st = n & 1, ph = (n >> 1) & 1;
+            if (pw == 0 && lane == 0) {
+                if (n + 1 < nsteps) {
+                    mbar_wait(BAR(3 + ((n + 1) & 1)), (((n + 1) >> 1) & 1) ^ 1);    // feature stage free
+                    issue_F(n + 1);
+                }
+                mbar_wait(BAR(11 + st), ph ^ 1);                                     // raw-cost stage free
+                issue_E(n);
+            }
+            __syncwarp();
+            if (n == 0) mbar_wait(BAR(0), 0);
+            mbar_wait(BAR(1 + st), ph);          // features of this window row have landed
+            mbar_wait(BAR(7 + st), ph ^ 1);      // consumers are done with this weight buffer
+
+            const float4 *f1 = reinterpret_cast<const float4 *>(smem + o_f1 + st * b_f1);
+            const float4 *f2 = reinterpret_cast<const float4 *>(smem + o_f2 + st * b_f2);
+            const float *parg = reinterpret_cast<const float *>(smem + o_pa + st * b_pa);
+            float *W1s = reinterpret_cast<float *>(smem + o_w1 + st * b_w1);
+            float *W2s = reinterpret_cast<float *>(smem + o_w2 + st * b_w2);
+            int cb = cb_begin, jb = jb_begin, left_pairs = p_end - p_begin;
+#pragma unroll 1
+            while (left_pairs > 0) {
+                // ---- per column block: centre, neighbour row, destination column ----
+                const bool right = cb < NCBR;                 // warp-uniform
+                const int col = (right ? cb : cb - NCBR) * 32 + lane;
+                // right: W2s[j][r], r reversed (xr = xr_max - r): centre NR-1-r, neighbour NR-1-r+j
+                //        (column r = NR is padding: it reads the float4 in front of C2s and is never used)
+                // left : W1s[j][x], centre (y, x0+x), neighbour (ii, x0+x-pad+j)
+                const int src = right ? NR - 1 - col : col;
+                const float4 c = right ? C2s[src] : C1s[src];
+                const int pitch = right ? NRp : T;
+                const float4 *nb = (right ? f2 : f1) + src + jb * 4;
+                const float *pa = parg + jb * 4;
+                float *dst = (right ? W2s : W1s) + col + jb * 4 * pitch;
+                const int jend = min(NB, jb + left_pairs);
+                left_pairs -= jend - jb;
+#pragma unroll 1
+                for (; jb < jend; ++jb) {
+                    // 4 window offsets: all loads first, stores last, so the exp/sqrt chains overlap.  Offsets past
+                    // the window (last batch) read finite padding of the staging buffers and are not stored.
+                    const float4 t = *reinterpret_cast<const float4 *>(pa);
+                    const float4 n0 = nb[0], n1 = nb[1], n2 = nb[2], n3 = nb[3];
+                    const float w0 = support_weight<false>(c, n0, P.kC, t.x);
+                    const float w1 = support_weight<false>(c, n1, P.kC, t.y);
+                    const float w2 = support_weight<false>(c, n2, P.kC, t.z);
+                    const float w3 = support_weight<false>(c, n3, P.kC, t.w);
+                    const int j0 = jb * 4;
+                    dst[0] = w0;
+                    if (j0 + 1 < win) dst[pitch] = w1;
+                    if (j0 + 2 < win) dst[2 * pitch] = w2;
+                    if (j0 + 3 < win) dst[3 * pitch] = w3;
+                    nb += 4;
+                    pa += 4;
+                    dst += 4 * pitch;
+                }
+                jb = 0;
+                ++cb;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(BAR(5 + st));        // weights ready
+                mbar_arrive(BAR(3 + st));        // feature stage may be refilled
+            }
+        }
+        return;
+    }
+
+    // =================================== consumers ===================================
+    if (DC == 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int dg = (warp % C::NDB) * 8 + (lane & 7);
+    const int xb = 8 * ((warp / C::NDB) * 4 + (lane >> 3));  // tile-relative first column
+    const int kb = 4 * dg;                                   // chunk-relative first disparity
+    const int R0 = T - 8 - xb + kb;                          // first reversed right-centre index (multiple of 4)
+
+    u64 acc0[8][2], acc1[8][2];                              // numerator, denominator
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) { acc0[a][b] = 0ull; acc1[a][b] = 0ull; }
+
+    for (int n = 0; n < nsteps; ++n) {
+        const int st = n & 1, ph = (n >> 1) & 1;
+        if (!P.freerun) {
+            mbar_wait(BAR(5 + st), ph);          // weights of this window row
+            mbar_wait(BAR(9 + st), ph);          // raw costs of this window row
+        }
+        {
+            u64 ring[8][2];
+            const uint8_t *ep = smem + (sp.e + st * sp.ebytes) + xb * EP + kb;
+#pragma unroll
+            for (int a = 0; a < 7; ++a) {
+                const uint32_t e = *reinterpret_cast<const uint32_t *>(ep + a * EP);
+                ring[a][0] = pk(u8_to_f32(e, 0), u8_to_f32(e, 1));
+                ring[a][1] = pk(u8_to_f32(e, 2), u8_to_f32(e, 3));
+            }
+            ep += 7 * EP;
+            const float *w1p = reinterpret_cast<const float *>(smem + (sp.w1 + st * sp.w1bytes)) + xb;
+            const float *w2p = reinterpret_cast<const float *>(smem + (sp.w2 + st * sp.w2bytes)) + R0;
+
+#ifdef SS_SCALAR
+            auto step = [&](auto sc) {
+                constexpr int s = decltype(sc)::value;
+                float *rf = reinterpret_cast<float *>(&ring[0][0]);
+                float *n0 = reinterpret_cast<float *>(&acc0[0][0]);
+                float *d0 = reinterpret_cast<float *>(&acc1[0][0]);
+                {
+                    const uint32_t e = *reinterpret_cast<const uint32_t *>(ep + s * EP);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) rf[((7 + s) & 7) * 4 + b] = u8_to_f32(e, b);
+                }
+                const float4 wa = *reinterpret_cast<const float4 *>(w1p + s * T);
+                const float4 wb = *reinterpret_cast<const float4 *>(w1p + s * T + 4);
+                const float4 v0 = *reinterpret_cast<const float4 *>(w2p + s * NRp);
+                const float4 v1 = *reinterpret_cast<const float4 *>(w2p + s * NRp + 4);
+                const float4 v2 = *reinterpret_cast<const float4 *>(w2p + s * NRp + 8);
+                const float w1[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                const float v[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const float ww = w1[a] * v[7 - a + b];
+                        n0[a * 4 + b] = fmaf(ww, rf[((a + s) & 7) * 4 + b], n0[a * 4 + b]);
+#if SS_SCALAR == 2
+                        d0[a * 4 + b] = fmaf(w1[a], v[7 - a + b], d0[a * 4 + b]);
+#else
+                        d0[a * 4 + b] += ww;
+#endif
+                    }
+            };
+#else
+            auto step = [&](auto sc) {
+                constexpr int s = decltype(sc)::value;
+                {
+                    const uint32_t e = *reinterpret_cast<const uint32_t *>(ep + s * EP);
+                    ring[(7 + s) & 7][0] = pk(u8_to_f32(e, 0), u8_to_f32(e, 1));
+                    ring[(7 + s) & 7][1] = pk(u8_to_f32(e, 2), u8_to_f32(e, 3));
+                }
+                const float4 wa = *reinterpret_cast<const float4 *>(w1p + s * T);
+                const float4 wb = *reinterpret_cast<const float4 *>(w1p + s * T + 4);
+                const float4 v0 = *reinterpret_cast<const float4 *>(w2p + s * NRp);
+                const float4 v1 = *reinterpret_cast<const float4 *>(w2p + s * NRp + 4);
+                const float4 v2 = *reinterpret_cast<const float4 *>(w2p + s * NRp + 8);
+                const float w1[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                const float v[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const u64 w1d = pk(w1[a], w1[a]);
+#pragma unroll
+                    for (int bp = 0; bp < 2; ++bp) {
+                        const u64 w2d = pk(v[7 - a + 2 * bp], v[8 - a + 2 * bp]);
+                        const u64 e2 = ring[(a + s) & 7][bp];
+                        const u64 ww = mul2(w1d, w2d);                  // w1*w2
+                        acc0[a][bp] = fma2(ww, e2, acc0[a][bp]);        // cost += w1*w2*e  (_passive.cpp:77)
+                        acc1[a][bp] = add2(acc1[a][bp], ww);            // tot  += w1*w2    (:82)
+                    }
+                }
+            };
+#endif
+            int j = 0;
+#pragma unroll 1
+            for (; j + 8 <= win; j += 8) {
+                step(IC<0>{}); step(IC<1>{}); step(IC<2>{}); step(IC<3>{});
+                step(IC<4>{}); step(IC<5>{}); step(IC<6>{}); step(IC<7>{});
+                ep += 8 * EP;
+                w1p += 8 * T;
+                w2p += 8 * NRp;
+            }
+            if (REM > 0) step(IC<0>{});
+            if (REM > 1) step(IC<1>{});
+            if (REM > 2) step(IC<2>{});
+            if (REM > 3) step(IC<3>{});
+            if (REM > 4) step(IC<4>{});
+            if (REM > 5) step(IC<5>{});
+            if (REM > 6) step(IC<6>{});
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(BAR(7 + st));            // weight buffer free
+            mbar_arrive(BAR(11 + st));           // raw-cost stage free
+        }
+    }
+
+    // ---- epilogue: normalise, WTA over the chunk, optional volume store --------------------------
+    const int rowo = y - g.row0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int x = x0 + xb + a;
+        float c0[4], c1[4];
+        upk(acc0[a][0], c0[0], c0[1]);
+        upk(acc0[a][1], c0[2], c0[3]);
+        upk(acc1[a][0], c1[0], c1[1]);
+        upk(acc1[a][1], c1[2], c1[3]);
+        u64 best = KEY_NONE;
+        float out0[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int d = dlo + kb + b;
+            const bool valid = (x < g.W) && (d <= g.dHi) && (x - d >= 0);
+            const float cost = __fdiv_rn(c0[b], c1[b]);                 // cost / tot (:88)
+            out0[b] = valid ? cost : INFINITY;
+            if (valid) {
+                const u64 k = make_key(cost, d);
+                best = k < best ? k : best;
+            }
+        }
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) {
+            const u64 o = __shfl_xor_sync(0xffffffffu, best, off);
+            best = o < best ? o : best;
+        }
+        if ((lane & 7) == 0 && x < g.W && best != KEY_NONE) atomicMin(P.bestL + (size_t)rowo * g.W + x, best);
+        if (x < g.W && P.vol0) {
+            const size_t o = ((size_t)rowo * g.W + x) * P.Dp + (size_t)ch * DC + kb;
+            *reinterpret_cast<float4 *>(P.vol0 + o) = make_float4(out0[0], out0[1], out0[2], out0[3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // k_wta_right: right-reference winners = minimum over diagonals of the aggregated volume
 // (_passive.cpp:209-248; d ascending, strict '<' => smallest disparity wins)
 // ------------------------------------------------------------------------------------------
@@ -723,6 +1100,7 @@ struct Ctx {
     double agg_ms_done = 0;
     long long agg_launches = 0, total_launches = 0;
     int smem_attr_val[2][12] = {};   // largest dynamic-smem opt-in set so far, per k_aggregate instantiation
+    int smem_attr_ws[12] = {};       // same for k_aggregate_ws
 };
 
 Ctx g_ctx;
@@ -789,6 +1167,7 @@ int ctx_init(int device) {
         c.stream = nullptr;
         c.prox_win = -1;
         memset(c.smem_attr_val, 0, sizeof(c.smem_attr_val));
+        memset(c.smem_attr_ws, 0, sizeof(c.smem_attr_ws));
     }
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
@@ -841,13 +1220,15 @@ Geom make_geom(const Call &q) {
     g.row0 = q.row0; g.row1 = q.row1;
     g.erow0 = q.row0 - g.pad < 0 ? 0 : q.row0 - g.pad;
     g.erow1 = q.row1 + g.pad > q.H ? q.H : q.row1 + g.pad;
-    g.ntx = (q.W + TILE_X - 1) / TILE_X;
-    g.UW = g.ntx * TILE_X + g.win - 1;
+    g.T = q.gsw ? TILE_X : TILE_WS;
+    g.EP = g.DC + 4;
+    g.ntx = (q.W + g.T - 1) / g.T;
+    g.UW = (g.ntx * g.T + g.win - 1 + 3) & ~3;
     g.PL2 = g.dLo + g.nch * g.DC - 1 + g.pad;
-    g.VW = g.ntx * TILE_X + g.pad + g.PL2;
-    g.NU = TILE_X + g.win - 1;
-    g.NR = TILE_X + g.DC - 1;
-    g.NRp = TILE_X + g.DC;
+    g.VW = g.ntx * g.T + g.pad + g.PL2;
+    g.NU = g.T + g.win - 1;
+    g.NR = g.T + g.DC - 1;
+    g.NRp = g.T + g.DC;
     g.NV = g.NR + g.win - 1;
     return g;
 }
@@ -877,6 +1258,44 @@ int launch_aggregate_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
     c.agg_launches++;
     c.total_launches++;
     return SS_OK;
+}
+
+template <int DC, int REM>
+int launch_ws_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
+    typedef WsCfg<DC> C;
+    const WsSmem sp = ws_smem(P.g.win, DC);
+    if (sp.total > 227 * 1024) return fail(SS_ERR_PARAM, "winSize too large for the shared-memory tiling of k_aggregate_ws");
+    const int di = (DC == 128 ? 2 : (DC == 64 ? 1 : 0)) * 4 + REM / 2;
+    if (c.smem_attr_ws[di] < sp.total) {
+        CU_TRY(cudaFuncSetAttribute(k_aggregate_ws<DC, REM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+        c.smem_attr_ws[di] = sp.total;
+    }
+    dim3 grid(P.g.ntx, P.g.row1 - P.g.row0, P.g.nch);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c.profile) {
+        CU_TRY(cudaEventCreate(&e0));
+        CU_TRY(cudaEventCreate(&e1));
+        CU_TRY(cudaEventRecord(e0, st));
+    }
+    k_aggregate_ws<DC, REM><<<grid, C::NT, sp.total, st>>>(P);
+    CU_TRY(cudaGetLastError());
+    if (c.profile) {
+        CU_TRY(cudaEventRecord(e1, st));
+        c.events.emplace_back(e0, e1);
+    }
+    c.agg_launches++;
+    c.total_launches++;
+    return SS_OK;
+}
+
+template <int DC>
+int launch_ws(Ctx &c, const AggParams &P, cudaStream_t st) {
+    switch (P.g.win & 7) {          // win is odd
+        case 1: return launch_ws_rem<DC, 1>(c, P, st);
+        case 3: return launch_ws_rem<DC, 3>(c, P, st);
+        case 5: return launch_ws_rem<DC, 5>(c, P, st);
+        default: return launch_ws_rem<DC, 7>(c, P, st);
+    }
 }
 
 template <bool GSW, int DC>
@@ -929,7 +1348,8 @@ int run_device(Ctx &c, const Call &q, const uint8_t *d_img1, const uint8_t *d_im
         int rc;
         if ((rc = ensure(c.f1, (size_t)erows * g.UW * 16))) return rc;
         if ((rc = ensure(c.f2, (size_t)erows * g.VW * 16))) return rc;
-        if ((rc = ensure(c.evol, (size_t)g.nch * erows * g.UW * g.DC * 4))) return rc;
+        if ((rc = ensure(c.evol, q.gsw ? (size_t)g.nch * erows * g.UW * g.DC * 4
+                                       : (size_t)g.nch * erows * g.UW * g.EP + 64))) return rc;
         const int Dp = g.nch * g.DC;
         const bool vol0 = need_right || o.want_vol0;
         if (vol0 && (rc = ensure(c.vol0, npx * Dp * 4))) return rc;
@@ -967,8 +1387,8 @@ int run_device(Ctx &c, const Call &q, const uint8_t *d_img1, const uint8_t *d_im
         {
             const int n = g.UW * (g.DC / 4);
             dim3 b(256), gr((n + 255) / 256, erows, g.nch);
-            if (q.gsw) k_cost_volume<true><<<gr, b, 0, st>>>(d_img1, d_img2, (float *)c.evol.p, g, q.fMax);
-            else k_cost_volume<false><<<gr, b, 0, st>>>(d_img1, d_img2, (float *)c.evol.p, g, 0.f);
+            if (q.gsw) k_cost_volume<true><<<gr, b, 0, st>>>(d_img1, d_img2, c.evol.p, g, q.fMax);
+            else k_cost_volume<false><<<gr, b, 0, st>>>(d_img1, d_img2, c.evol.p, g, 0.f);
             CU_TRY(cudaGetLastError());
             c.total_launches += 1;
         }
@@ -976,7 +1396,7 @@ int run_device(Ctx &c, const Call &q, const uint8_t *d_img1, const uint8_t *d_im
         P.g = g;
         P.F1 = (const float4 *)c.f1.p;
         P.F2 = (const float4 *)c.f2.p;
-        P.E = (const float *)c.evol.p;
+        P.E = c.evol.p;
         P.proxarg = (const float *)c.prox.p;
         P.kC = q.gsw ? (float)q.gamma : (float)(-1.4426950408889634 / q.gammaC);
         P.iterations = q.iterations;
@@ -984,6 +1404,7 @@ int run_device(Ctx &c, const Call &q, const uint8_t *d_img1, const uint8_t *d_im
         P.vol0 = vol0 ? (float *)c.vol0.p : nullptr;
         P.vol1 = o.want_vol1 ? (float *)c.vol1.p : nullptr;
         P.Dp = Dp;
+        P.freerun = getenv("SS_FREERUN") ? atoi(getenv("SS_FREERUN")) : 0;
 #ifdef SS_DEBUG_DUMP
         P.dbg = g_dbg;
 #endif
@@ -992,9 +1413,9 @@ int run_device(Ctx &c, const Call &q, const uint8_t *d_img1, const uint8_t *d_im
             else if (g.DC == 64) rc = launch_aggregate<true, 64>(c, P, st);
             else rc = launch_aggregate<true, 32>(c, P, st);
         } else {
-            if (g.DC == 128) rc = launch_aggregate<false, 128>(c, P, st);
-            else if (g.DC == 64) rc = launch_aggregate<false, 64>(c, P, st);
-            else rc = launch_aggregate<false, 32>(c, P, st);
+            if (g.DC == 128) rc = launch_ws<128>(c, P, st);
+            else if (g.DC == 64) rc = launch_ws<64>(c, P, st);
+            else rc = launch_ws<32>(c, P, st);
         }
         if (rc) return rc;
         if (need_right && keysR) {
@@ -1131,6 +1552,7 @@ int ss_shutdown(void) {
     c.prox_win = -1;
     c.ready = false;
     memset(c.smem_attr_val, 0, sizeof(c.smem_attr_val));
+    memset(c.smem_attr_ws, 0, sizeof(c.smem_attr_ws));
     return SS_OK;
 }
 
