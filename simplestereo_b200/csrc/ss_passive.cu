@@ -861,13 +861,17 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
                 const float4 v1 = *reinterpret_cast<const float4 *>(w2p + s * NRp + 4);
                 const float4 v2 = *reinterpret_cast<const float4 *>(w2p + s * NRp + 8);
                 const float w1[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-                const float v[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+                // right-weight pairs (v[k], v[k+1]): even k are the register pairs the loads produced, odd k
+                // straddle two of them and cost two moves each -- built once per step, not once per use
+                const u64 VA[6] = {pk(v0.x, v0.y), pk(v0.z, v0.w), pk(v1.x, v1.y), pk(v1.z, v1.w), pk(v2.x, v2.y), pk(v2.z, v2.w)};
+                const u64 VM[5] = {pk(v0.y, v0.z), pk(v0.w, v1.x), pk(v1.y, v1.z), pk(v1.w, v2.x), pk(v2.y, v2.z)};
 #pragma unroll
                 for (int a = 0; a < 8; ++a) {
                     const u64 w1d = pk(w1[a], w1[a]);
 #pragma unroll
                     for (int bp = 0; bp < 2; ++bp) {
-                        const u64 w2d = pk(v[7 - a + 2 * bp], v[8 - a + 2 * bp]);
+                        const int k = 7 - a + 2 * bp;                   // reversed right index of disparity kb+2bp
+                        const u64 w2d = (k & 1) ? VM[k >> 1] : VA[k >> 1];
                         const u64 e2 = ring[(a + s) & 7][bp];
                         const u64 ww = mul2(w1d, w2d);                  // w1*w2
                         acc0[a][bp] = fma2(ww, e2, acc0[a][bp]);        // cost += w1*w2*e  (_passive.cpp:77)
