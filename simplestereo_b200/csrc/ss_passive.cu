@@ -107,6 +107,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// same, for waits that are expected to be long (producers waiting for a free buffer): back off between polls so
+// the polling warp does not take issue slots from the arithmetic warps
+__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
+#ifdef SS_SLEEP_NS
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(SS_SLEEP_NS);
+    }
+#else
+    mbar_wait(bar, parity);
+#endif
+}
 // TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -601,7 +623,9 @@ struct WsSmem {         // stage s of a double-buffered region lives at base + s
     int e, f1, f2, pa, c1, c2, w1, w2, bars, total;
     int ebytes, f1bytes, f2bytes, pabytes, w1bytes, w2bytes;
 };
-__host__ __device__ inline WsSmem ws_smem(int win, int DC) {
+__host__ __device__ inline WsSmem ws_smem(int win, int DC, int mode) {
+    const bool dual = mode == 1;
+    const int wstages = mode == 2 ? 3 : 2;
     const int T = TILE_WS, NU = T + win - 1, NR = T + DC - 1, NRp = T + DC, NV = NR + win - 1, EP = DC + 4;
     const int winq = (win + 3) >> 2;
     WsSmem p;
@@ -611,15 +635,15 @@ __host__ __device__ inline WsSmem ws_smem(int win, int DC) {
     p.f2bytes = NV * 16;
     p.pabytes = winq * 16;
     p.w1bytes = (win * T * 4 + 15) & ~15;
-    p.w2bytes = (win * NRp * 4 + 15) & ~15;
+    p.w2bytes = ((win * NRp * 4 + 15) & ~15) * (dual ? 2 : 1);   // dual: [V | V shifted by one column]
     p.e = off;  off += 2 * p.ebytes;
     p.f1 = off; off += 2 * p.f1bytes;
     p.f2 = off; off += 2 * p.f2bytes;
     p.pa = off; off += 2 * p.pabytes;
     p.c1 = off; off += T * 16;
     p.c2 = off; off += NRp * 16;
-    p.w1 = off; off += 2 * p.w1bytes;
-    p.w2 = off; off += 2 * p.w2bytes;
+    p.w1 = off; off += wstages * p.w1bytes;
+    p.w2 = off; off += wstages * p.w2bytes;
     p.bars = off; off += 16 * 8;
     p.total = off;
     return p;
@@ -635,8 +659,15 @@ __device__ __forceinline__ float u8_to_f32(uint32_t w, int byte) {
     return f;
 }
 
-template <int DC, int REM>
+// DUAL: the right-weight rows are stored twice, the second copy shifted by one column, so that BOTH parities of
+// the (v[k], v[k+1]) pairs the packed multiply needs are 8-byte aligned register pairs straight out of LDS.128
+// (otherwise every odd-k pair costs two register moves per step: 20 of 80 consumer instructions).
+// MODE 0: one copy, 2 weight stages (large windows) | 1: dual copy, 2 stages | 2: one copy, 3 stages (absorbs
+// the skew between consumer warps: producers may run two window rows ahead)
+template <int DC, int REM, int MODE>
 __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws(const AggParams P) {
+    constexpr bool DUAL = MODE == 1;
+    constexpr int NWS = MODE == 2 ? 3 : 2;
     typedef WsCfg<DC> C;
     constexpr int T = C::T, NRp = C::NRp, EP = C::EP, CW = C::CW, PW = C::PW;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -644,10 +675,11 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
     const Geom &g = P.g;
     const int win = g.win, pad = g.pad;
     const int NU = g.NU, NR = g.NR, NV = g.NV;
-    const WsSmem sp = ws_smem(win, DC);
+    const WsSmem sp = ws_smem(win, DC, MODE);
     const int winq = (win + 3) >> 2, winp = winq * 4;
+    const int w2copy = (win * NRp * 4 + 15) & ~15;              // bytes of one right-weight copy
     const uint32_t bar0 = smem_u32(smem + sp.bars);
-    // barrier slots: 0 centres | 1,2 fullF | 3,4 emptyF | 5,6 fullW | 7,8 emptyW | 9,10 fullE | 11,12 emptyE
+    // barrier slots: 0 centres | 1,2 fullF | 3,4 emptyF | 5-7 fullW | 8-10 emptyW | 11,12 fullE | 13,14 emptyE
     auto BAR = [&](int slot) { return bar0 + 8u * (uint32_t)slot; };
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -664,10 +696,12 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
         for (int s = 0; s < 2; ++s) {
             mbar_init(BAR(1 + s), 1);
             mbar_init(BAR(3 + s), PW);
+            mbar_init(BAR(11 + s), 1);
+            mbar_init(BAR(13 + s), CW);
+        }
+        for (int s = 0; s < NWS; ++s) {
             mbar_init(BAR(5 + s), PW);
-            mbar_init(BAR(7 + s), CW);
-            mbar_init(BAR(9 + s), 1);
-            mbar_init(BAR(11 + s), CW);
+            mbar_init(BAR(8 + s), CW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -675,7 +709,12 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
 
     if (warp >= CW) {
         // =================================== producers ===================================
+#ifdef SS_BATCH8
+        if (DC == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+#else
         if (DC == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+#endif
+
         if (P.freerun) return;
         const int pw = warp - CW;
         const int f2_start = x0 - dlo - DC + 1 - pad + g.PL2;
@@ -694,7 +733,7 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
         };
         auto issue_E = [&](int n) {
             const int ii = y - pad + i_lo + n, st = n & 1;
-            const uint32_t bar = BAR(9 + st);
+            const uint32_t bar = BAR(11 + st);
             mbar_expect_tx(bar, (uint32_t)sp.ebytes);
             tma_load_1d(smem_u32(smem + (sp.e + st * sp.ebytes)),
                         static_cast<const uint8_t *>(P.E) + ((size_t)ch * erows + (ii - g.erow0)) * e_plane + (size_t)x0 * EP,
@@ -716,26 +755,27 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
         const int o_f1 = sp.f1, o_f2 = sp.f2, o_pa = sp.pa, o_w1 = sp.w1, o_w2 = sp.w2;
         const int b_f1 = sp.f1bytes, b_f2 = sp.f2bytes, b_pa = sp.pabytes, b_w1 = sp.w1bytes, b_w2 = sp.w2bytes;
 
+        int sw = 0, phw = 0;                                // weight stage and its phase
         for (int n = 0; n < nsteps; ++n) {
             const int st = n & 1, ph = (n >> 1) & 1;
             if (pw == 0 && lane == 0) {
                 if (n + 1 < nsteps) {
-                    mbar_wait(BAR(3 + ((n + 1) & 1)), (((n + 1) >> 1) & 1) ^ 1);    // feature stage free
+                    mbar_wait_long(BAR(3 + ((n + 1) & 1)), (((n + 1) >> 1) & 1) ^ 1);    // feature stage free
                     issue_F(n + 1);
                 }
-                mbar_wait(BAR(11 + st), ph ^ 1);                                     // raw-cost stage free
+                mbar_wait_long(BAR(13 + st), ph ^ 1);                                // raw-cost stage free
                 issue_E(n);
             }
             __syncwarp();
             if (n == 0) mbar_wait(BAR(0), 0);
             mbar_wait(BAR(1 + st), ph);          // features of this window row have landed
-            mbar_wait(BAR(7 + st), ph ^ 1);      // consumers are done with this weight buffer
+            mbar_wait_long(BAR(8 + sw), phw ^ 1); // consumers are done with this weight buffer
 
             const float4 *f1 = reinterpret_cast<const float4 *>(smem + o_f1 + st * b_f1);
             const float4 *f2 = reinterpret_cast<const float4 *>(smem + o_f2 + st * b_f2);
             const float *parg = reinterpret_cast<const float *>(smem + o_pa + st * b_pa);
-            float *W1s = reinterpret_cast<float *>(smem + o_w1 + st * b_w1);
-            float *W2s = reinterpret_cast<float *>(smem + o_w2 + st * b_w2);
+            float *W1s = reinterpret_cast<float *>(smem + o_w1 + sw * b_w1);
+            float *W2s = reinterpret_cast<float *>(smem + o_w2 + sw * b_w2);
             int cb = cb_begin, jb = jb_begin, left_pairs = p_end - p_begin;
 #pragma unroll 1
             while (left_pairs > 0) {
@@ -753,42 +793,89 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
                 float *dst = (right ? W2s : W1s) + col + jb * 4 * pitch;
                 const int jend = min(NB, jb + left_pairs);
                 left_pairs -= jend - jb;
+                // batches of 4 window offsets, two batches in flight: all loads first, stores last, so eight
+                // exp/sqrt chains overlap.  Offsets past the window (last batch) read finite padding of the staging
+                // buffers and are not stored.
+                auto store4 = [&](float *d, int j0, float w0, float w1, float w2, float w3) {
+                    d[0] = w0;
+                    if (j0 + 1 < win) d[pitch] = w1;
+                    if (j0 + 2 < win) d[2 * pitch] = w2;
+                    if (j0 + 3 < win) d[3 * pitch] = w3;
+                    if (DUAL && right && col > 0) {          // shifted copy: B[j][r-1] = V[j][r]
+                        float *dB = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(d) + w2copy) - 1;
+                        dB[0] = w0;
+                        if (j0 + 1 < win) dB[pitch] = w1;
+                        if (j0 + 2 < win) dB[2 * pitch] = w2;
+                        if (j0 + 3 < win) dB[3 * pitch] = w3;
+                    }
+                };
+#ifdef SS_BATCH8
 #pragma unroll 1
-                for (; jb < jend; ++jb) {
-                    // 4 window offsets: all loads first, stores last, so the exp/sqrt chains overlap.  Offsets past
-                    // the window (last batch) read finite padding of the staging buffers and are not stored.
+                for (; jb + 2 <= jend; jb += 2) {
+                    const float4 t0 = *reinterpret_cast<const float4 *>(pa);
+                    const float4 t1 = *reinterpret_cast<const float4 *>(pa + 4);
+                    const float4 n0 = nb[0], n1 = nb[1], n2 = nb[2], n3 = nb[3];
+                    const float4 n4 = nb[4], n5 = nb[5], n6 = nb[6], n7 = nb[7];
+                    const float w0 = support_weight<false>(c, n0, P.kC, t0.x);
+                    const float w1 = support_weight<false>(c, n1, P.kC, t0.y);
+                    const float w2 = support_weight<false>(c, n2, P.kC, t0.z);
+                    const float w3 = support_weight<false>(c, n3, P.kC, t0.w);
+                    const float w4 = support_weight<false>(c, n4, P.kC, t1.x);
+                    const float w5 = support_weight<false>(c, n5, P.kC, t1.y);
+                    const float w6 = support_weight<false>(c, n6, P.kC, t1.z);
+                    const float w7 = support_weight<false>(c, n7, P.kC, t1.w);
+                    store4(dst, jb * 4, w0, w1, w2, w3);
+                    store4(dst + 4 * pitch, jb * 4 + 4, w4, w5, w6, w7);
+                    nb += 8;
+                    pa += 8;
+                    dst += 8 * pitch;
+                }
+                if (jb < jend) {
+#else
+#pragma unroll 1
+                for (; jb < jend;) {
+#endif
                     const float4 t = *reinterpret_cast<const float4 *>(pa);
                     const float4 n0 = nb[0], n1 = nb[1], n2 = nb[2], n3 = nb[3];
                     const float w0 = support_weight<false>(c, n0, P.kC, t.x);
                     const float w1 = support_weight<false>(c, n1, P.kC, t.y);
                     const float w2 = support_weight<false>(c, n2, P.kC, t.z);
                     const float w3 = support_weight<false>(c, n3, P.kC, t.w);
-                    const int j0 = jb * 4;
-                    dst[0] = w0;
-                    if (j0 + 1 < win) dst[pitch] = w1;
-                    if (j0 + 2 < win) dst[2 * pitch] = w2;
-                    if (j0 + 3 < win) dst[3 * pitch] = w3;
+                    store4(dst, jb * 4, w0, w1, w2, w3);
                     nb += 4;
                     pa += 4;
                     dst += 4 * pitch;
+                    ++jb;
                 }
                 jb = 0;
                 ++cb;
             }
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(BAR(5 + st));        // weights ready
+                mbar_arrive(BAR(5 + sw));        // weights ready
                 mbar_arrive(BAR(3 + st));        // feature stage may be refilled
             }
+            if (++sw == NWS) { sw = 0; phw ^= 1; }
         }
         return;
     }
 
     // =================================== consumers ===================================
+#ifdef SS_BATCH8
+    if (DC == 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
+#else
     if (DC == 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+#endif
+
+    // Lane -> register tile: a warp is 4 x-groups (of 8 columns) x 8 disparity groups (of 4).
+    const int xg = (warp / C::NDB) * 4 + (lane >> 3);
     const int dg = (warp % C::NDB) * 8 + (lane & 7);
-    const int xb = 8 * ((warp / C::NDB) * 4 + (lane >> 3));  // tile-relative first column
+    const int xb = 8 * xg;                                   // tile-relative first column
     const int kb = 4 * dg;                                   // chunk-relative first disparity
+    // A warp whose 32 x 32 (x, d) rectangle holds no evaluated pair (x - d < 0 everywhere, at the left image border,
+    // or d beyond the requested range) only keeps the barriers moving.
+    const int wx1 = x0 + 32 * (warp / C::NDB) + 31, wd0 = dlo + 32 * (warp % C::NDB);
+    const bool warp_live = (wx1 >= wd0) && (wd0 <= g.dHi) && (x0 + 32 * (warp / C::NDB) < g.W);
     const int R0 = T - 8 - xb + kb;                          // first reversed right-centre index (multiple of 4)
 
     u64 acc0[8][2], acc1[8][2];                              // numerator, denominator
@@ -797,13 +884,14 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
 #pragma unroll
         for (int b = 0; b < 2; ++b) { acc0[a][b] = 0ull; acc1[a][b] = 0ull; }
 
+    int sw = 0, phw = 0;                                     // weight stage and its phase
     for (int n = 0; n < nsteps; ++n) {
         const int st = n & 1, ph = (n >> 1) & 1;
         if (!P.freerun) {
-            mbar_wait(BAR(5 + st), ph);          // weights of this window row
-            mbar_wait(BAR(9 + st), ph);          // raw costs of this window row
+            mbar_wait(BAR(5 + sw), phw);         // weights of this window row
+            mbar_wait(BAR(11 + st), ph);         // raw costs of this window row
         }
-        {
+        if (warp_live) {
             u64 ring[8][2];
             const uint8_t *ep = smem + (sp.e + st * sp.ebytes) + xb * EP + kb;
 #pragma unroll
@@ -813,8 +901,8 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
                 ring[a][1] = pk(u8_to_f32(e, 2), u8_to_f32(e, 3));
             }
             ep += 7 * EP;
-            const float *w1p = reinterpret_cast<const float *>(smem + (sp.w1 + st * sp.w1bytes)) + xb;
-            const float *w2p = reinterpret_cast<const float *>(smem + (sp.w2 + st * sp.w2bytes)) + R0;
+            const float *w1p = reinterpret_cast<const float *>(smem + (sp.w1 + sw * sp.w1bytes)) + xb;
+            const float *w2p = reinterpret_cast<const float *>(smem + (sp.w2 + sw * sp.w2bytes)) + R0;
 
 #ifdef SS_SCALAR
             auto step = [&](auto sc) {
@@ -861,10 +949,19 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
                 const float4 v1 = *reinterpret_cast<const float4 *>(w2p + s * NRp + 4);
                 const float4 v2 = *reinterpret_cast<const float4 *>(w2p + s * NRp + 8);
                 const float w1[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-                // right-weight pairs (v[k], v[k+1]): even k are the register pairs the loads produced, odd k
-                // straddle two of them and cost two moves each -- built once per step, not once per use
+                // right-weight pairs (v[k], v[k+1]): even k are the register pairs the loads produced; odd k either
+                // come from the shifted copy (DUAL) or straddle two loads and cost two moves each
                 const u64 VA[6] = {pk(v0.x, v0.y), pk(v0.z, v0.w), pk(v1.x, v1.y), pk(v1.z, v1.w), pk(v2.x, v2.y), pk(v2.z, v2.w)};
-                const u64 VM[5] = {pk(v0.y, v0.z), pk(v0.w, v1.x), pk(v1.y, v1.z), pk(v1.w, v2.x), pk(v2.y, v2.z)};
+                u64 VM[5];
+                if (DUAL) {
+                    const float *w2b = reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(w2p) + w2copy);
+                    const float4 u0 = *reinterpret_cast<const float4 *>(w2b + s * NRp);
+                    const float4 u1 = *reinterpret_cast<const float4 *>(w2b + s * NRp + 4);
+                    const float2 u2 = *reinterpret_cast<const float2 *>(w2b + s * NRp + 8);
+                    VM[0] = pk(u0.x, u0.y); VM[1] = pk(u0.z, u0.w); VM[2] = pk(u1.x, u1.y); VM[3] = pk(u1.z, u1.w); VM[4] = pk(u2.x, u2.y);
+                } else {
+                    VM[0] = pk(v0.y, v0.z); VM[1] = pk(v0.w, v1.x); VM[2] = pk(v1.y, v1.z); VM[3] = pk(v1.w, v2.x); VM[4] = pk(v2.y, v2.z);
+                }
 #pragma unroll
                 for (int a = 0; a < 8; ++a) {
                     const u64 w1d = pk(w1[a], w1[a]);
@@ -899,9 +996,10 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
         }
         __syncwarp();
         if (lane == 0) {
-            mbar_arrive(BAR(7 + st));            // weight buffer free
-            mbar_arrive(BAR(11 + st));           // raw-cost stage free
+            mbar_arrive(BAR(8 + sw));            // weight buffer free
+            mbar_arrive(BAR(13 + st));           // raw-cost stage free
         }
+        if (++sw == NWS) { sw = 0; phw ^= 1; }
     }
 
     // ---- epilogue: normalise, WTA over the chunk, optional volume store --------------------------
@@ -1104,7 +1202,7 @@ struct Ctx {
     double agg_ms_done = 0;
     long long agg_launches = 0, total_launches = 0;
     int smem_attr_val[2][12] = {};   // largest dynamic-smem opt-in set so far, per k_aggregate instantiation
-    int smem_attr_ws[12] = {};       // same for k_aggregate_ws
+    int smem_attr_ws[36] = {};       // same for k_aggregate_ws
 };
 
 Ctx g_ctx;
@@ -1264,14 +1362,14 @@ int launch_aggregate_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
     return SS_OK;
 }
 
-template <int DC, int REM>
+template <int DC, int REM, int MODE>
 int launch_ws_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
     typedef WsCfg<DC> C;
-    const WsSmem sp = ws_smem(P.g.win, DC);
+    const WsSmem sp = ws_smem(P.g.win, DC, MODE);
     if (sp.total > 227 * 1024) return fail(SS_ERR_PARAM, "winSize too large for the shared-memory tiling of k_aggregate_ws");
-    const int di = (DC == 128 ? 2 : (DC == 64 ? 1 : 0)) * 4 + REM / 2;
+    const int di = ((DC == 128 ? 2 : (DC == 64 ? 1 : 0)) * 4 + REM / 2) * 3 + MODE;
     if (c.smem_attr_ws[di] < sp.total) {
-        CU_TRY(cudaFuncSetAttribute(k_aggregate_ws<DC, REM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+        CU_TRY(cudaFuncSetAttribute(k_aggregate_ws<DC, REM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
         c.smem_attr_ws[di] = sp.total;
     }
     dim3 grid(P.g.ntx, P.g.row1 - P.g.row0, P.g.nch);
@@ -1281,7 +1379,7 @@ int launch_ws_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
         CU_TRY(cudaEventCreate(&e1));
         CU_TRY(cudaEventRecord(e0, st));
     }
-    k_aggregate_ws<DC, REM><<<grid, C::NT, sp.total, st>>>(P);
+    k_aggregate_ws<DC, REM, MODE><<<grid, C::NT, sp.total, st>>>(P);
     CU_TRY(cudaGetLastError());
     if (c.profile) {
         CU_TRY(cudaEventRecord(e1, st));
@@ -1292,14 +1390,27 @@ int launch_ws_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
     return SS_OK;
 }
 
+template <int DC, int MODE>
+int launch_ws_mode(Ctx &c, const AggParams &P, cudaStream_t st) {
+    switch (P.g.win & 7) {          // win is odd
+        case 1: return launch_ws_rem<DC, 1, MODE>(c, P, st);
+        case 3: return launch_ws_rem<DC, 3, MODE>(c, P, st);
+        case 5: return launch_ws_rem<DC, 5, MODE>(c, P, st);
+        default: return launch_ws_rem<DC, 7, MODE>(c, P, st);
+    }
+}
+
 template <int DC>
 int launch_ws(Ctx &c, const AggParams &P, cudaStream_t st) {
-    switch (P.g.win & 7) {          // win is odd
-        case 1: return launch_ws_rem<DC, 1>(c, P, st);
-        case 3: return launch_ws_rem<DC, 3>(c, P, st);
-        case 5: return launch_ws_rem<DC, 5>(c, P, st);
-        default: return launch_ws_rem<DC, 7>(c, P, st);
+    // weight-buffer organisation, best first, limited by the per-SM share of shared memory
+    const int budget = 227 * 1024 / WsCfg<DC>::MINB - 1024;
+    int mode = getenv("SS_WS_MODE") ? atoi(getenv("SS_WS_MODE")) : -1;
+    if (mode < 0 || mode > 2 || ws_smem(P.g.win, DC, mode).total > budget) {
+        mode = ws_smem(P.g.win, DC, 1).total <= budget ? 1 : 0;
     }
+    if (mode == 2) return launch_ws_mode<DC, 2>(c, P, st);
+    if (mode == 1) return launch_ws_mode<DC, 1>(c, P, st);
+    return launch_ws_mode<DC, 0>(c, P, st);
 }
 
 template <bool GSW, int DC>
