@@ -265,7 +265,8 @@ struct AggParams {
     const float4 *F2;     // right features [erows][VW]
     const void *E;        // raw cost volume: GSW float [nch][erows][UW][DC]; ASW uint8 [nch][erows][UW][EP]
     const float *proxarg; // ASW: -log2(e)*r/gammaP per window offset [win][(win+3)&~3]
-    float kC;             // ASW: -log2(e)/gammaC ; GSW: (float)gamma
+    float kC;             // ASW: -log2(e)/gammaC ; GSW (k_aggregate): (float)gamma
+    float kC2;            // GSW (k_aggregate_ws): -log2(e)/gamma
     int iterations;       // GSW only (<=0: centre weight only)
     u64 *bestL;           // [(row1-row0)*W] packed (cost,disp) keys, atomicMin
     float *vol0;          // optional: ASW cost / GSW right cost  [(rows)*W*Dp]
@@ -608,25 +609,33 @@ __global__ void __launch_bounds__(AggCfg<DC>::NT, AggCfg<DC>::MINB) k_aggregate(
 // (setmaxnreg), which removes the spills of the 128-register version.
 // ------------------------------------------------------------------------------------------
 
-template <int DC> struct WsCfg {
-    static constexpr int T = TILE_WS;
+template <bool GSW, int DC> struct WsCfg {
+    static constexpr int T = GSW ? TILE_X : TILE_WS;   // GSW keeps float raw costs in shared memory: 64-column tiles
+    static constexpr int XB = T / 32;            // blocks of 32 output columns
     static constexpr int NDB = DC / 32;          // blocks of 32 disparities (8 groups of 4)
-    static constexpr int CW = 3 * NDB;           // consumer warps
-    static constexpr int PW = NDB;               // producer warps
-    static constexpr int NT = (CW + PW) * 32;    // 512 / 256 / 128 threads
-    static constexpr int MINB = 4 / NDB;         // 1 / 2 / 4 blocks per SM
+    static constexpr int CW = XB * NDB;          // consumer warps
+#ifndef SS_GSW_PW
+#define SS_GSW_PW 2
+#endif
+    // producer warps: GSW has fewer consumer warps per block (2 per scheduler), so the weight rows are tabulated
+    // by two producer warps per scheduler or the consumers wait for them (ncu: 45 % of consumer samples)
+    static constexpr int PW = GSW ? SS_GSW_PW * NDB : NDB;
+    static constexpr int NT = (CW + PW) * 32;    // ASW 512 / 256 / 128 threads, GSW 512 / 256 / 128
+    static constexpr int MINB = GSW ? 1 : 4 / NDB;   // blocks per SM the register budget is sized for
     static constexpr int NRp = T + DC;
-    static constexpr int EP = DC + 4;            // bytes per raw-cost column
+    static constexpr int EP = GSW ? DC * 4 : DC + 4;   // bytes per raw-cost column (ASW: bytes, skewed by 4)
+    static constexpr bool SETREG = DC == 128 && NT == 512;   // 16 warps: producers give registers to the consumers
 };
 
 struct WsSmem {         // stage s of a double-buffered region lives at base + s * size
     int e, f1, f2, pa, c1, c2, w1, w2, bars, total;
     int ebytes, f1bytes, f2bytes, pabytes, w1bytes, w2bytes;
 };
-__host__ __device__ inline WsSmem ws_smem(int win, int DC, int mode) {
+__host__ __device__ inline WsSmem ws_smem(int win, int DC, int mode, bool gsw) {
     const bool dual = mode == 1;
     const int wstages = mode == 2 ? 3 : 2;
-    const int T = TILE_WS, NU = T + win - 1, NR = T + DC - 1, NRp = T + DC, NV = NR + win - 1, EP = DC + 4;
+    const int T = gsw ? TILE_X : TILE_WS, NU = T + win - 1, NR = T + DC - 1, NRp = T + DC, NV = NR + win - 1;
+    const int EP = gsw ? DC * 4 : DC + 4;
     const int winq = (win + 3) >> 2;
     WsSmem p;
     int off = 0;
@@ -664,18 +673,18 @@ __device__ __forceinline__ float u8_to_f32(uint32_t w, int byte) {
 // (otherwise every odd-k pair costs two register moves per step: 20 of 80 consumer instructions).
 // MODE 0: one copy, 2 weight stages (large windows) | 1: dual copy, 2 stages | 2: one copy, 3 stages (absorbs
 // the skew between consumer warps: producers may run two window rows ahead)
-template <int DC, int REM, int MODE>
-__global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws(const AggParams P) {
+template <bool GSW, int DC, int REM, int MODE>
+__global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_aggregate_ws(const AggParams P) {
     constexpr bool DUAL = MODE == 1;
     constexpr int NWS = MODE == 2 ? 3 : 2;
-    typedef WsCfg<DC> C;
+    typedef WsCfg<GSW, DC> C;
     constexpr int T = C::T, NRp = C::NRp, EP = C::EP, CW = C::CW, PW = C::PW;
     extern __shared__ __align__(128) unsigned char smem[];
 
     const Geom &g = P.g;
     const int win = g.win, pad = g.pad;
     const int NU = g.NU, NR = g.NR, NV = g.NV;
-    const WsSmem sp = ws_smem(win, DC, MODE);
+    const WsSmem sp = ws_smem(win, DC, MODE, GSW);
     const int winq = (win + 3) >> 2, winp = winq * 4;
     const int w2copy = (win * NRp * 4 + 15) & ~15;              // bytes of one right-weight copy
     const uint32_t bar0 = smem_u32(smem + sp.bars);
@@ -709,11 +718,7 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
 
     if (warp >= CW) {
         // =================================== producers ===================================
-#ifdef SS_BATCH8
-        if (DC == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-#else
-        if (DC == 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-#endif
+        if (C::SETREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
 
         if (P.freerun) return;
         const int pw = warp - CW;
@@ -726,10 +731,10 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
         auto issue_F = [&](int n) {
             const int i = i_lo + n, ii = y - pad + i, st = n & 1;
             const uint32_t bar = BAR(1 + st);
-            mbar_expect_tx(bar, (uint32_t)((NU + NV + winq) * 16));
+            mbar_expect_tx(bar, (uint32_t)((NU + NV + (GSW ? 0 : winq)) * 16));
             tma_load_1d(smem_u32(smem + (sp.f1 + st * sp.f1bytes)), P.F1 + (size_t)(ii - g.erow0) * g.UW + x0, NU * 16, bar);
             tma_load_1d(smem_u32(smem + (sp.f2 + st * sp.f2bytes)), P.F2 + (size_t)(ii - g.erow0) * g.VW + f2_start, NV * 16, bar);
-            tma_load_1d(smem_u32(smem + (sp.pa + st * sp.pabytes)), P.proxarg + (size_t)i * winp, winq * 16, bar);
+            if (!GSW) tma_load_1d(smem_u32(smem + (sp.pa + st * sp.pabytes)), P.proxarg + (size_t)i * winp, winq * 16, bar);
         };
         auto issue_E = [&](int n) {
             const int ii = y - pad + i_lo + n, st = n & 1;
@@ -809,38 +814,34 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
                         if (j0 + 3 < win) dB[3 * pitch] = w3;
                     }
                 };
-#ifdef SS_BATCH8
-#pragma unroll 1
-                for (; jb + 2 <= jend; jb += 2) {
-                    const float4 t0 = *reinterpret_cast<const float4 *>(pa);
-                    const float4 t1 = *reinterpret_cast<const float4 *>(pa + 4);
-                    const float4 n0 = nb[0], n1 = nb[1], n2 = nb[2], n3 = nb[3];
-                    const float4 n4 = nb[4], n5 = nb[5], n6 = nb[6], n7 = nb[7];
-                    const float w0 = support_weight<false>(c, n0, P.kC, t0.x);
-                    const float w1 = support_weight<false>(c, n1, P.kC, t0.y);
-                    const float w2 = support_weight<false>(c, n2, P.kC, t0.z);
-                    const float w3 = support_weight<false>(c, n3, P.kC, t0.w);
-                    const float w4 = support_weight<false>(c, n4, P.kC, t1.x);
-                    const float w5 = support_weight<false>(c, n5, P.kC, t1.y);
-                    const float w6 = support_weight<false>(c, n6, P.kC, t1.z);
-                    const float w7 = support_weight<false>(c, n7, P.kC, t1.w);
-                    store4(dst, jb * 4, w0, w1, w2, w3);
-                    store4(dst + 4 * pitch, jb * 4 + 4, w4, w5, w6, w7);
-                    nb += 8;
-                    pa += 8;
-                    dst += 8 * pitch;
-                }
-                if (jb < jend) {
-#else
 #pragma unroll 1
                 for (; jb < jend;) {
-#endif
-                    const float4 t = *reinterpret_cast<const float4 *>(pa);
                     const float4 n0 = nb[0], n1 = nb[1], n2 = nb[2], n3 = nb[3];
-                    const float w0 = support_weight<false>(c, n0, P.kC, t.x);
-                    const float w1 = support_weight<false>(c, n1, P.kC, t.y);
-                    const float w2 = support_weight<false>(c, n2, P.kC, t.z);
-                    const float w3 = support_weight<false>(c, n3, P.kC, t.w);
+                    float w0, w1, w2, w3;
+                    if (GSW) {
+                        // closed form of the relaxation: exp(-||I(q) - I(centre)|| / gamma)
+                        w0 = support_weight<false>(c, n0, P.kC2, 0.f);
+                        w1 = support_weight<false>(c, n1, P.kC2, 0.f);
+                        w2 = support_weight<false>(c, n2, P.kC2, 0.f);
+                        w3 = support_weight<false>(c, n3, P.kC2, 0.f);
+                        // iterations <= 0: only the centre keeps weight 1.  Right-border abort of the LEFT pass
+                        // (_passive.cpp:445-446, :470-471): centre only, or the centre row when y == 0.
+                        const bool crow = (i_lo + n) == pad;
+                        const bool qk = !right && (x0 + col + pad >= g.W);
+                        const int j0 = jb * 4;
+                        if (P.iterations <= 0 || (qk && !(y == 0 && crow))) {
+                            w0 = (crow && j0 == pad) ? 1.f : 0.f;
+                            w1 = (crow && j0 + 1 == pad) ? 1.f : 0.f;
+                            w2 = (crow && j0 + 2 == pad) ? 1.f : 0.f;
+                            w3 = (crow && j0 + 3 == pad) ? 1.f : 0.f;
+                        }
+                    } else {
+                        const float4 t = *reinterpret_cast<const float4 *>(pa);
+                        w0 = support_weight<false>(c, n0, P.kC, t.x);
+                        w1 = support_weight<false>(c, n1, P.kC, t.y);
+                        w2 = support_weight<false>(c, n2, P.kC, t.z);
+                        w3 = support_weight<false>(c, n3, P.kC, t.w);
+                    }
                     store4(dst, jb * 4, w0, w1, w2, w3);
                     nb += 4;
                     pa += 4;
@@ -861,11 +862,7 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
     }
 
     // =================================== consumers ===================================
-#ifdef SS_BATCH8
-    if (DC == 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
-#else
-    if (DC == 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
-#endif
+    if (C::SETREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
 
     // Lane -> register tile: a warp is 4 x-groups (of 8 columns) x 8 disparity groups (of 4).
     const int xg = (warp / C::NDB) * 4 + (lane >> 3);
@@ -893,56 +890,28 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
         }
         if (warp_live) {
             u64 ring[8][2];
-            const uint8_t *ep = smem + (sp.e + st * sp.ebytes) + xb * EP + kb;
+            // raw costs of column c, disparities kb..kb+3: ASW 4 bytes (I2F.U8 on the XU pipe), GSW one float4
+            const uint8_t *ep = smem + (sp.e + st * sp.ebytes) + xb * EP + kb * (GSW ? 4 : 1);
+            auto load_e = [&](const uint8_t *q, u64 &lo, u64 &hi) {
+                if (GSW) {
+                    const float4 e = *reinterpret_cast<const float4 *>(q);
+                    lo = pk(e.x, e.y);
+                    hi = pk(e.z, e.w);
+                } else {
+                    const uint32_t e = *reinterpret_cast<const uint32_t *>(q);
+                    lo = pk(u8_to_f32(e, 0), u8_to_f32(e, 1));
+                    hi = pk(u8_to_f32(e, 2), u8_to_f32(e, 3));
+                }
+            };
 #pragma unroll
-            for (int a = 0; a < 7; ++a) {
-                const uint32_t e = *reinterpret_cast<const uint32_t *>(ep + a * EP);
-                ring[a][0] = pk(u8_to_f32(e, 0), u8_to_f32(e, 1));
-                ring[a][1] = pk(u8_to_f32(e, 2), u8_to_f32(e, 3));
-            }
+            for (int a = 0; a < 7; ++a) load_e(ep + a * EP, ring[a][0], ring[a][1]);
             ep += 7 * EP;
             const float *w1p = reinterpret_cast<const float *>(smem + (sp.w1 + sw * sp.w1bytes)) + xb;
             const float *w2p = reinterpret_cast<const float *>(smem + (sp.w2 + sw * sp.w2bytes)) + R0;
 
-#ifdef SS_SCALAR
             auto step = [&](auto sc) {
                 constexpr int s = decltype(sc)::value;
-                float *rf = reinterpret_cast<float *>(&ring[0][0]);
-                float *n0 = reinterpret_cast<float *>(&acc0[0][0]);
-                float *d0 = reinterpret_cast<float *>(&acc1[0][0]);
-                {
-                    const uint32_t e = *reinterpret_cast<const uint32_t *>(ep + s * EP);
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) rf[((7 + s) & 7) * 4 + b] = u8_to_f32(e, b);
-                }
-                const float4 wa = *reinterpret_cast<const float4 *>(w1p + s * T);
-                const float4 wb = *reinterpret_cast<const float4 *>(w1p + s * T + 4);
-                const float4 v0 = *reinterpret_cast<const float4 *>(w2p + s * NRp);
-                const float4 v1 = *reinterpret_cast<const float4 *>(w2p + s * NRp + 4);
-                const float4 v2 = *reinterpret_cast<const float4 *>(w2p + s * NRp + 8);
-                const float w1[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-                const float v[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-#pragma unroll
-                for (int a = 0; a < 8; ++a)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const float ww = w1[a] * v[7 - a + b];
-                        n0[a * 4 + b] = fmaf(ww, rf[((a + s) & 7) * 4 + b], n0[a * 4 + b]);
-#if SS_SCALAR == 2
-                        d0[a * 4 + b] = fmaf(w1[a], v[7 - a + b], d0[a * 4 + b]);
-#else
-                        d0[a * 4 + b] += ww;
-#endif
-                    }
-            };
-#else
-            auto step = [&](auto sc) {
-                constexpr int s = decltype(sc)::value;
-                {
-                    const uint32_t e = *reinterpret_cast<const uint32_t *>(ep + s * EP);
-                    ring[(7 + s) & 7][0] = pk(u8_to_f32(e, 0), u8_to_f32(e, 1));
-                    ring[(7 + s) & 7][1] = pk(u8_to_f32(e, 2), u8_to_f32(e, 3));
-                }
+                load_e(ep + s * EP, ring[(7 + s) & 7][0], ring[(7 + s) & 7][1]);
                 const float4 wa = *reinterpret_cast<const float4 *>(w1p + s * T);
                 const float4 wb = *reinterpret_cast<const float4 *>(w1p + s * T + 4);
                 const float4 v0 = *reinterpret_cast<const float4 *>(w2p + s * NRp);
@@ -970,13 +939,17 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
                         const int k = 7 - a + 2 * bp;                   // reversed right index of disparity kb+2bp
                         const u64 w2d = (k & 1) ? VM[k >> 1] : VA[k >> 1];
                         const u64 e2 = ring[(a + s) & 7][bp];
-                        const u64 ww = mul2(w1d, w2d);                  // w1*w2
-                        acc0[a][bp] = fma2(ww, e2, acc0[a][bp]);        // cost += w1*w2*e  (_passive.cpp:77)
-                        acc1[a][bp] = add2(acc1[a][bp], ww);            // tot  += w1*w2    (:82)
+                        if (GSW) {
+                            acc0[a][bp] = fma2(w1d, e2, acc0[a][bp]);   // left-reference cost  (_passive.cpp:528)
+                            acc1[a][bp] = fma2(w2d, e2, acc1[a][bp]);   // right-reference cost (:644)
+                        } else {
+                            const u64 ww = mul2(w1d, w2d);              // w1*w2
+                            acc0[a][bp] = fma2(ww, e2, acc0[a][bp]);    // cost += w1*w2*e  (_passive.cpp:77)
+                            acc1[a][bp] = add2(acc1[a][bp], ww);        // tot  += w1*w2    (:82)
+                        }
                     }
                 }
             };
-#endif
             int j = 0;
 #pragma unroll 1
             for (; j + 8 <= win; j += 8) {
@@ -1013,13 +986,15 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
         upk(acc1[a][0], c1[0], c1[1]);
         upk(acc1[a][1], c1[2], c1[3]);
         u64 best = KEY_NONE;
-        float out0[4];
+        float out0[4], out1[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int d = dlo + kb + b;
             const bool valid = (x < g.W) && (d <= g.dHi) && (x - d >= 0);
-            const float cost = __fdiv_rn(c0[b], c1[b]);                 // cost / tot (:88)
-            out0[b] = valid ? cost : INFINITY;
+            // ASW: cost / tot (:88), one volume serves both references; GSW: un-normalised left / right sums
+            const float cost = GSW ? c0[b] : __fdiv_rn(c0[b], c1[b]);
+            out0[b] = valid ? (GSW ? c1[b] : cost) : INFINITY;
+            out1[b] = valid ? cost : INFINITY;
             if (valid) {
                 const u64 k = make_key(cost, d);
                 best = k < best ? k : best;
@@ -1031,9 +1006,10 @@ __global__ void __launch_bounds__(WsCfg<DC>::NT, WsCfg<DC>::MINB) k_aggregate_ws
             best = o < best ? o : best;
         }
         if ((lane & 7) == 0 && x < g.W && best != KEY_NONE) atomicMin(P.bestL + (size_t)rowo * g.W + x, best);
-        if (x < g.W && P.vol0) {
+        if (x < g.W) {
             const size_t o = ((size_t)rowo * g.W + x) * P.Dp + (size_t)ch * DC + kb;
-            *reinterpret_cast<float4 *>(P.vol0 + o) = make_float4(out0[0], out0[1], out0[2], out0[3]);
+            if (P.vol0) *reinterpret_cast<float4 *>(P.vol0 + o) = make_float4(out0[0], out0[1], out0[2], out0[3]);
+            if (GSW && P.vol1) *reinterpret_cast<float4 *>(P.vol1 + o) = make_float4(out1[0], out1[1], out1[2], out1[3]);
         }
     }
 }
@@ -1202,7 +1178,7 @@ struct Ctx {
     double agg_ms_done = 0;
     long long agg_launches = 0, total_launches = 0;
     int smem_attr_val[2][12] = {};   // largest dynamic-smem opt-in set so far, per k_aggregate instantiation
-    int smem_attr_ws[36] = {};       // same for k_aggregate_ws
+    int smem_attr_ws[72] = {};       // same for k_aggregate_ws
 };
 
 Ctx g_ctx;
@@ -1362,14 +1338,14 @@ int launch_aggregate_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
     return SS_OK;
 }
 
-template <int DC, int REM, int MODE>
+template <bool GSW, int DC, int REM, int MODE>
 int launch_ws_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
-    typedef WsCfg<DC> C;
-    const WsSmem sp = ws_smem(P.g.win, DC, MODE);
+    typedef WsCfg<GSW, DC> C;
+    const WsSmem sp = ws_smem(P.g.win, DC, MODE, GSW);
     if (sp.total > 227 * 1024) return fail(SS_ERR_PARAM, "winSize too large for the shared-memory tiling of k_aggregate_ws");
-    const int di = ((DC == 128 ? 2 : (DC == 64 ? 1 : 0)) * 4 + REM / 2) * 3 + MODE;
+    const int di = (((DC == 128 ? 2 : (DC == 64 ? 1 : 0)) * 4 + REM / 2) * 3 + MODE) * 2 + (GSW ? 1 : 0);
     if (c.smem_attr_ws[di] < sp.total) {
-        CU_TRY(cudaFuncSetAttribute(k_aggregate_ws<DC, REM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+        CU_TRY(cudaFuncSetAttribute(k_aggregate_ws<GSW, DC, REM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
         c.smem_attr_ws[di] = sp.total;
     }
     dim3 grid(P.g.ntx, P.g.row1 - P.g.row0, P.g.nch);
@@ -1379,7 +1355,7 @@ int launch_ws_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
         CU_TRY(cudaEventCreate(&e1));
         CU_TRY(cudaEventRecord(e0, st));
     }
-    k_aggregate_ws<DC, REM, MODE><<<grid, C::NT, sp.total, st>>>(P);
+    k_aggregate_ws<GSW, DC, REM, MODE><<<grid, C::NT, sp.total, st>>>(P);
     CU_TRY(cudaGetLastError());
     if (c.profile) {
         CU_TRY(cudaEventRecord(e1, st));
@@ -1390,27 +1366,30 @@ int launch_ws_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
     return SS_OK;
 }
 
-template <int DC, int MODE>
+template <bool GSW, int DC, int MODE>
 int launch_ws_mode(Ctx &c, const AggParams &P, cudaStream_t st) {
     switch (P.g.win & 7) {          // win is odd
-        case 1: return launch_ws_rem<DC, 1, MODE>(c, P, st);
-        case 3: return launch_ws_rem<DC, 3, MODE>(c, P, st);
-        case 5: return launch_ws_rem<DC, 5, MODE>(c, P, st);
-        default: return launch_ws_rem<DC, 7, MODE>(c, P, st);
+        case 1: return launch_ws_rem<GSW, DC, 1, MODE>(c, P, st);
+        case 3: return launch_ws_rem<GSW, DC, 3, MODE>(c, P, st);
+        case 5: return launch_ws_rem<GSW, DC, 5, MODE>(c, P, st);
+        default: return launch_ws_rem<GSW, DC, 7, MODE>(c, P, st);
     }
 }
 
-template <int DC>
+// true when the warp-specialised kernel can stage this window in shared memory at all
+bool ws_fits(int win, int DC, bool gsw) { return ws_smem(win, DC, 0, gsw).total <= 227 * 1024; }
+
+template <bool GSW, int DC>
 int launch_ws(Ctx &c, const AggParams &P, cudaStream_t st) {
     // weight-buffer organisation, best first, limited by the per-SM share of shared memory
-    const int budget = 227 * 1024 / WsCfg<DC>::MINB - 1024;
+    const int budget = 227 * 1024 / WsCfg<GSW, DC>::MINB - 1024;
     int mode = getenv("SS_WS_MODE") ? atoi(getenv("SS_WS_MODE")) : -1;
-    if (mode < 0 || mode > 2 || ws_smem(P.g.win, DC, mode).total > budget) {
-        mode = ws_smem(P.g.win, DC, 1).total <= budget ? 1 : 0;
+    if (mode < 0 || mode > 2 || ws_smem(P.g.win, DC, mode, GSW).total > budget) {
+        mode = ws_smem(P.g.win, DC, 1, GSW).total <= budget ? 1 : 0;
     }
-    if (mode == 2) return launch_ws_mode<DC, 2>(c, P, st);
-    if (mode == 1) return launch_ws_mode<DC, 1>(c, P, st);
-    return launch_ws_mode<DC, 0>(c, P, st);
+    if (mode == 2) return launch_ws_mode<GSW, DC, 2>(c, P, st);
+    if (mode == 1) return launch_ws_mode<GSW, DC, 1>(c, P, st);
+    return launch_ws_mode<GSW, DC, 0>(c, P, st);
 }
 
 template <bool GSW, int DC>
@@ -1514,6 +1493,7 @@ int run_device(Ctx &c, const Call &q, const uint8_t *d_img1, const uint8_t *d_im
         P.E = c.evol.p;
         P.proxarg = (const float *)c.prox.p;
         P.kC = q.gsw ? (float)q.gamma : (float)(-1.4426950408889634 / q.gammaC);
+        P.kC2 = q.gsw ? (float)(-1.4426950408889634 / (double)q.gamma) : 0.f;
         P.iterations = q.iterations;
         P.bestL = keysL;
         P.vol0 = vol0 ? (float *)c.vol0.p : nullptr;
@@ -1523,14 +1503,21 @@ int run_device(Ctx &c, const Call &q, const uint8_t *d_img1, const uint8_t *d_im
 #ifdef SS_DEBUG_DUMP
         P.dbg = g_dbg;
 #endif
-        if (q.gsw) {
+        const bool gsw_ws = q.gsw && ws_fits(q.win, g.DC, true) && !(getenv("SS_GSW_SINGLE") && atoi(getenv("SS_GSW_SINGLE")));
+        if (q.gsw && !gsw_ws) {
+            // single-role kernel: exact expf / IEEE sqrt weights; also the path for windows whose float raw-cost
+            // tiles do not fit the double-buffered staging of the warp-specialised kernel
             if (g.DC == 128) rc = launch_aggregate<true, 128>(c, P, st);
             else if (g.DC == 64) rc = launch_aggregate<true, 64>(c, P, st);
             else rc = launch_aggregate<true, 32>(c, P, st);
+        } else if (q.gsw) {
+            if (g.DC == 128) rc = launch_ws<true, 128>(c, P, st);
+            else if (g.DC == 64) rc = launch_ws<true, 64>(c, P, st);
+            else rc = launch_ws<true, 32>(c, P, st);
         } else {
-            if (g.DC == 128) rc = launch_ws<128>(c, P, st);
-            else if (g.DC == 64) rc = launch_ws<64>(c, P, st);
-            else rc = launch_ws<32>(c, P, st);
+            if (g.DC == 128) rc = launch_ws<false, 128>(c, P, st);
+            else if (g.DC == 64) rc = launch_ws<false, 64>(c, P, st);
+            else rc = launch_ws<false, 32>(c, P, st);
         }
         if (rc) return rc;
         if (need_right && keysR) {
