@@ -146,19 +146,61 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled every 10 ms
+    from a thread (nvidia_ml_py), falling back to `nvidia-smi -lms` when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         self.index = index
-        self.rows = []
+        self.uuid = uuid
+        self.rows = []          # (sm_mhz, reasons bitmask or list of names)
+        self.max_mhz = None
         self.proc = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.uuid:
+            for cand in (f"GPU-{self.uuid}", str(self.uuid)):
+                try:
+                    return pynvml, pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if hasattr(cand, "encode") else cand)
+                except Exception:
+                    continue
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def start(self):
         try:
+            nv, h = self._nvml_handle()
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                     ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                     ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+
+            def poll():
+                while not self.stop_flag.is_set():
+                    try:
+                        mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                        mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.rows.append((mhz, [n for n, bit in names if mask & bit]))
+                    except Exception:
+                        pass
+                    self.stop_flag.wait(0.01)
+
+            self.source = "nvml"
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -166,27 +208,36 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) < 9:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9 or not c[1].replace(".", "").isdigit():
                 continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if r[col].lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            if c[2].replace(".", "").isdigit():
+                self.max_mhz = max(self.max_mhz or 0.0, float(c[2]))
+            reasons = [n for n, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8))
+                       if c[col].lower().startswith("active")]
+            self.rows.append((float(c[1]), reasons))
+
+    def mark(self):
+        """Index of the next sample: brackets the timed region inside a longer sampling run."""
+        return len(self.rows)
+
+    def stop(self, first=0, last=None):
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        rows = self.rows[first:last] or self.rows
+        sm = [r[0] for r in rows]
+        reasons = sorted({n for r in rows for n in r[1]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "source": self.source}
 
 
 def run_b200(args):
@@ -243,11 +294,16 @@ def run_b200(args):
     # ---- device-timed leg -------------------------------------------------------------------------
     L.ss_profile_reset()
     L.ss_profile_enable(1)
-    sampler = ClockSampler(local)
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid)
     if rank == 0:
         sampler.start()
     evs = []
     barrier()
+    s_first = sampler.mark()
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.fill_(0)                        # L2 flush between timed iterations (not timed)
@@ -258,7 +314,7 @@ def run_b200(args):
         evs.append((e0, e1))
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(s_first, sampler.mark()) if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:

@@ -46,6 +46,18 @@ namespace {
 
 typedef unsigned long long u64;
 
+#ifndef SS_PADROWS
+#define SS_PADROWS 1
+#endif
+#ifndef SS_SHEAR
+#define SS_SHEAR 1
+#endif
+#ifndef SS_UNROLL
+#define SS_UNROLL 2            // periods (8 window columns) per trip of the consumer loop: 1, 2 or 4
+#endif
+#ifndef SS_WAIT_HINT
+#define SS_WAIT_HINT 1000000   // mbarrier.try_wait suspend-time hint (ns); 0 = plain polling
+#endif
 constexpr int TILE_X = 64;          // output columns per block of k_aggregate (GSW)
 constexpr int TILE_WS = 96;         // output columns per block of k_aggregate_ws (ASW)
 constexpr float SENTINEL = 1.0e18f; // feature value of out-of-image pixels
@@ -95,6 +107,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if SS_WAIT_HINT
+    // the suspend-time hint keeps a waiting warp parked in hardware instead of re-issuing the poll: polling
+    // loops were 18 % of all issued instructions (ncu) and compete with the warps that are being waited for
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity), "r"((uint32_t)SS_WAIT_HINT)
+        : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -106,6 +133,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar),
         "r"(parity)
         : "memory");
+#endif
 }
 // same, for waits that are expected to be long (producers waiting for a free buffer): back off between polls so
 // the polling warp does not take issue slots from the arithmetic warps
@@ -643,8 +671,9 @@ __host__ __device__ inline WsSmem ws_smem(int win, int DC, int mode, bool gsw) {
     p.f1bytes = NU * 16;
     p.f2bytes = NV * 16;
     p.pabytes = winq * 16;
-    p.w1bytes = (win * T * 4 + 15) & ~15;
-    p.w2bytes = ((win * NRp * 4 + 15) & ~15) * (dual ? 2 : 1);   // dual: [V | V shifted by one column]
+    const int winr = SS_PADROWS ? (win + 3) & ~3 : win;          // weight rows per buffer
+    p.w1bytes = (winr * T * 4 + 15) & ~15;
+    p.w2bytes = ((winr * NRp * 4 + 15) & ~15) * (dual ? 2 : 1);  // dual: [V | V shifted by one column]
     p.e = off;  off += 2 * p.ebytes;
     p.f1 = off; off += 2 * p.f1bytes;
     p.f2 = off; off += 2 * p.f2bytes;
@@ -686,7 +715,7 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
     const int NU = g.NU, NR = g.NR, NV = g.NV;
     const WsSmem sp = ws_smem(win, DC, MODE, GSW);
     const int winq = (win + 3) >> 2, winp = winq * 4;
-    const int w2copy = (win * NRp * 4 + 15) & ~15;              // bytes of one right-weight copy
+    const int w2copy = ((SS_PADROWS ? (win + 3) & ~3 : win) * NRp * 4 + 15) & ~15;   // bytes of one right-weight copy
     const uint32_t bar0 = smem_u32(smem + sp.bars);
     // barrier slots: 0 centres | 1,2 fullF | 3,4 emptyF | 5-7 fullW | 8-10 emptyW | 11,12 fullE | 13,14 emptyE
     auto BAR = [&](int slot) { return bar0 + 8u * (uint32_t)slot; };
@@ -801,17 +830,19 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
                 // batches of 4 window offsets, two batches in flight: all loads first, stores last, so eight
                 // exp/sqrt chains overlap.  Offsets past the window (last batch) read finite padding of the staging
                 // buffers and are not stored.
+                // SS_PADROWS: the weight buffers hold (win + 3) & ~3 rows, so a batch of 4 is stored without
+                // predicates (rows past the window are written with finite junk and never read)
                 auto store4 = [&](float *d, int j0, float w0, float w1, float w2, float w3) {
                     d[0] = w0;
-                    if (j0 + 1 < win) d[pitch] = w1;
-                    if (j0 + 2 < win) d[2 * pitch] = w2;
-                    if (j0 + 3 < win) d[3 * pitch] = w3;
+                    if (SS_PADROWS || j0 + 1 < win) d[pitch] = w1;
+                    if (SS_PADROWS || j0 + 2 < win) d[2 * pitch] = w2;
+                    if (SS_PADROWS || j0 + 3 < win) d[3 * pitch] = w3;
                     if (DUAL && right && col > 0) {          // shifted copy: B[j][r-1] = V[j][r]
                         float *dB = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(d) + w2copy) - 1;
                         dB[0] = w0;
-                        if (j0 + 1 < win) dB[pitch] = w1;
-                        if (j0 + 2 < win) dB[2 * pitch] = w2;
-                        if (j0 + 3 < win) dB[3 * pitch] = w3;
+                        if (SS_PADROWS || j0 + 1 < win) dB[pitch] = w1;
+                        if (SS_PADROWS || j0 + 2 < win) dB[2 * pitch] = w2;
+                        if (SS_PADROWS || j0 + 3 < win) dB[3 * pitch] = w3;
                     }
                 };
 #pragma unroll 1
@@ -865,14 +896,22 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
     if (C::SETREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
 
     // Lane -> register tile: a warp is 4 x-groups (of 8 columns) x 8 disparity groups (of 4).
-    const int xg = (warp / C::NDB) * 4 + (lane >> 3);
-    const int dg = (warp % C::NDB) * 8 + (lane & 7);
+    // The d-groups of x-group xl are rotated by 2*xl (mod DC/4): the right-weight index R0 = T-8-xb+kb is then the
+    // same for the four quarter-warps, so one LDS.128 of a right-weight row is ONE 128-byte wavefront for the warp
+    // instead of four overlapping ones (shared-memory wavefronts, not issue slots, were the co-limiter: ncu 79 %).
+    const int xl = lane >> 3, dl = lane & 7;
+    const int xg = (warp / C::NDB) * 4 + xl;
+#if SS_SHEAR
+    const int dg = ((warp % C::NDB) * 8 + dl + 2 * xl) % (DC / 4);
+#else
+    const int dg = (warp % C::NDB) * 8 + dl;
+#endif
     const int xb = 8 * xg;                                   // tile-relative first column
     const int kb = 4 * dg;                                   // chunk-relative first disparity
-    // A warp whose 32 x 32 (x, d) rectangle holds no evaluated pair (x - d < 0 everywhere, at the left image border,
-    // or d beyond the requested range) only keeps the barriers moving.
-    const int wx1 = x0 + 32 * (warp / C::NDB) + 31, wd0 = dlo + 32 * (warp % C::NDB);
-    const bool warp_live = (wx1 >= wd0) && (wd0 <= g.dHi) && (x0 + 32 * (warp / C::NDB) < g.W);
+    // A warp none of whose lane tiles holds an evaluated pair (x - d < 0 everywhere, at the left image border, or d
+    // beyond the requested range) only keeps the barriers moving.
+    const bool lane_live = (x0 + xb < g.W) && (dlo + kb <= g.dHi) && (x0 + xb + 7 >= dlo + kb);
+    const bool warp_live = __any_sync(0xffffffffu, lane_live);
     const int R0 = T - 8 - xb + kb;                          // first reversed right-centre index (multiple of 4)
 
     u64 acc0[8][2], acc1[8][2];                              // numerator, denominator
@@ -951,14 +990,22 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
                 }
             };
             int j = 0;
-#pragma unroll 1
-            for (; j + 8 <= win; j += 8) {
+            // SS_UNROLL periods of 8 window columns per loop trip: ptxas needs ~50 loop-carried register moves per
+            // trip (ring + prefetched loads), so two periods per trip issue fewer instructions (-5 % time at C2)
+            auto period = [&]() {
                 step(IC<0>{}); step(IC<1>{}); step(IC<2>{}); step(IC<3>{});
                 step(IC<4>{}); step(IC<5>{}); step(IC<6>{}); step(IC<7>{});
                 ep += 8 * EP;
                 w1p += 8 * T;
                 w2p += 8 * NRp;
+            };
+#pragma unroll 1
+            for (; j + 8 * SS_UNROLL <= win; j += 8 * SS_UNROLL) {
+#pragma unroll
+                for (int u = 0; u < SS_UNROLL; ++u) period();
             }
+            if (SS_UNROLL > 2 && j + 16 <= win) { period(); period(); j += 16; }
+            if (SS_UNROLL > 1 && j + 8 <= win) { period(); j += 8; }
             if (REM > 0) step(IC<0>{});
             if (REM > 1) step(IC<1>{});
             if (REM > 2) step(IC<2>{});
@@ -1384,9 +1431,9 @@ int launch_ws(Ctx &c, const AggParams &P, cudaStream_t st) {
     // weight-buffer organisation, best first, limited by the per-SM share of shared memory
     const int budget = 227 * 1024 / WsCfg<GSW, DC>::MINB - 1024;
     int mode = getenv("SS_WS_MODE") ? atoi(getenv("SS_WS_MODE")) : -1;
-    if (mode < 0 || mode > 2 || ws_smem(P.g.win, DC, mode, GSW).total > budget) {
-        mode = ws_smem(P.g.win, DC, 1, GSW).total <= budget ? 1 : 0;
-    }
+    // default: single right-weight copy (mode 0).  The dual copy trades 10 register moves per step for three more
+    // shared-memory loads and doubles the producers' stores; measured 4 % slower at C2 (9.95 vs 9.58 ms).
+    if (mode < 0 || mode > 2 || ws_smem(P.g.win, DC, mode, GSW).total > budget) mode = 0;
     if (mode == 2) return launch_ws_mode<GSW, DC, 2>(c, P, st);
     if (mode == 1) return launch_ws_mode<GSW, DC, 1>(c, P, st);
     return launch_ws_mode<GSW, DC, 0>(c, P, st);
