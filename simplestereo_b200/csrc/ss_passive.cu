@@ -300,6 +300,7 @@ struct AggParams {
     float *vol0;          // optional: ASW cost / GSW right cost  [(rows)*W*Dp]
     float *vol1;          // optional: GSW left cost
     int Dp;               // pitch of vol0/vol1 (= nch*DC)
+    int vol_export;       // the volumes are returned to the caller (debug export): unevaluated pairs must read +inf
     int freerun;          // timing experiment (SS_FREERUN=1): consumers ignore the barriers, producers idle; results are garbage
 #ifdef SS_DEBUG_DUMP
     float *dbg;           // [0]=bx [1]=by [2]=step ; dump of W1s, W2s, Es of that block/step follows at dbg+16
@@ -728,6 +729,23 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
     const int erows = g.erow1 - g.erow0;
     const int i_lo = max(0, pad - y), i_hi = min(win - 1, g.H - 1 - y + pad);
     const int nsteps = i_hi - i_lo + 1;
+
+    // Tiles left of the chunk's first disparity hold no evaluated pair (x - d < 0 everywhere): at D = 512 that is 4 %
+    // of the blocks.  Their winner keys stay KEY_NONE; the volumes are only touched when they are exported.
+    if (x0 + T - 1 < dlo) {
+        if (P.vol_export) {
+            const int rowo = y - g.row0;
+            for (int k = tid; k < T * (DC / 4); k += C::NT) {
+                const int x = x0 + k / (DC / 4), kq = (k % (DC / 4)) * 4;
+                if (x >= g.W) continue;
+                const size_t o = ((size_t)rowo * g.W + x) * P.Dp + (size_t)ch * DC + kq;
+                const float4 inf4 = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+                if (P.vol0) *reinterpret_cast<float4 *>(P.vol0 + o) = inf4;
+                if (P.vol1) *reinterpret_cast<float4 *>(P.vol1 + o) = inf4;
+            }
+        }
+        return;
+    }
 
     if (tid == 0) {
         mbar_init(BAR(0), 1);
@@ -1546,6 +1564,7 @@ int run_device(Ctx &c, const Call &q, const uint8_t *d_img1, const uint8_t *d_im
         P.vol0 = vol0 ? (float *)c.vol0.p : nullptr;
         P.vol1 = o.want_vol1 ? (float *)c.vol1.p : nullptr;
         P.Dp = Dp;
+        P.vol_export = (o.want_vol0 || o.want_vol1) ? 1 : 0;
         P.freerun = getenv("SS_FREERUN") ? atoi(getenv("SS_FREERUN")) : 0;
 #ifdef SS_DEBUG_DUMP
         P.dbg = g_dbg;

@@ -275,3 +275,58 @@ def test_row_stripes_device_entry_point():
         _cabi.check(L.ss_gsw_compute_device(dl.data_ptr(), dr.data_ptr(), w, h, *m._args(), r0, r1, got[r0:r1].data_ptr(), st))
     torch.cuda.synchronize()
     assert np.array_equal(got.cpu().numpy(), want)
+
+
+# ---- BASELINE.json configs C4 / C5 at FULL size: size-independent properties + oracle rows ------------------
+
+def test_c4_full_size_middlebury_lr_consistency():
+    """C4: 2880x1988, 256 disparities, win 51, L-R check.  Full frame on the GPU; three rows against the oracle
+    (which reads the full-height window), row stripes bit-identical to the full-frame call, ground truth recovered."""
+    l, r, gt = synth_pair(2880, 1988, 255, 2)
+    kw = dict(winSize=51, maxDisparity=255, minDisparity=0, gammaC=5, gammaP=17.5, consistent=True)
+    m = ss.passive.StereoASW(**kw)
+    gpu = m.compute_staged(l, r)
+    rows = (1000, 1002)
+    ref = oracle.asw(l, r, stages=True, cost=True, rows=rows, **kw)
+    sl = slice(*rows)
+    g = {k: gpu[k][sl] for k in ("left", "right", "invalid", "final")}
+    rr = {k: ref[k][sl] for k in ("left", "right", "invalid", "final")}
+    parity.check_staged(g, rr, ref["cost"], ref["cost"], 0, True)
+    for r0, r1 in ((0, 3), (994, 1003), (1985, 1988)):
+        assert np.array_equal(m.compute(l, r, rows=(r0, r1)), gpu["final"][r0:r1])
+    assert (gpu["left"] == gt).mean() > 0.85
+    assert gpu["final"].min() >= 0 and gpu["final"].max() <= 255
+
+
+def test_c5_full_size_4k_disparity_shards_equal_unsharded():
+    """C5: 3840x2160, 512 disparities.  Eight disparity-range shards (the 8-GPU partition, emulated on one GPU
+    through ss_asw_partial_device / ss_merge_keys_device / ss_finalize_keys_device) == the unsharded call,
+    bit for bit; two rows against the oracle; ground truth recovered."""
+    import torch
+    from simplestereo_b200 import _cabi
+    from simplestereo_b200.sharding import disparity_shards
+    l, r, gt = synth_pair(3840, 2160, 511, 3)
+    h, w = l.shape[:2]
+    kw = dict(winSize=35, maxDisparity=511, minDisparity=0, gammaC=5, gammaP=17.5, consistent=False)
+    m = ss.passive.StereoASW(**kw)
+    want = m.compute(l, r)
+    L = _cabi.lib()
+    dl, dr = torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()
+    n = 8
+    keys = torch.empty((n, h * w), dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for k, (d0, d1) in enumerate(disparity_shards(0, 511, n)):
+        _cabi.check(L.ss_asw_partial_device(dl.data_ptr(), dr.data_ptr(), w, h, 35, 511, 0, 5.0, 17.5, 0, 0, h, d0, d1,
+                                            keys[k].data_ptr(), None, st))
+    _cabi.check(L.ss_merge_keys_device(keys.data_ptr(), n, h * w, st))
+    out = torch.empty((h, w), dtype=torch.int16, device="cuda")
+    _cabi.check(L.ss_finalize_keys_device(keys[0].data_ptr(), None, w, h, 0, out.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)
+    del keys, out, dl, dr
+    torch.cuda.empty_cache()
+    rows = (1080, 1081)
+    ref = oracle.asw(l, r, stages=True, cost=True, rows=rows, **kw)
+    parity.adjudicate_left(want[rows[0]:rows[1]], ref["left"][rows[0]:rows[1]], ref["cost"], 0)
+    assert (want == gt).mean() > 0.80
+    assert want.min() >= 0 and want.max() <= 511
