@@ -24,6 +24,9 @@ SYMBOLS = (
     "ss_asw_partial_device", "ss_merge_keys_device", "ss_finalize_keys_device",
     "ss_asw_stages", "ss_gsw_stages",
     "ss_profile_enable", "ss_profile_read", "ss_profile_reset", "ss_measure_fp32_peak",
+    # include/ss_post.h
+    "ss_reproject", "ss_reproject_device", "ss_asw_compute_points",
+    "ss_normalize_colormap", "ss_normalize_colormap_device", "ss_remap_linear", "ss_remap_linear_device",
 )
 
 _lib = None
@@ -67,6 +70,14 @@ def lib():
     L.ss_profile_read.argtypes = [ctypes.POINTER(c_dbl), ctypes.POINTER(c_ll), ctypes.POINTER(c_ll)]
     L.ss_profile_reset.argtypes = []
     L.ss_measure_fp32_peak.argtypes = [ctypes.POINTER(c_dbl), c_vp]
+    # include/ss_post.h
+    L.ss_reproject.argtypes = [c_vp, c_int, c_int, c_vp, c_vp]
+    L.ss_reproject_device.argtypes = [c_vp, c_int, c_int, c_vp, c_vp, c_vp]
+    L.ss_asw_compute_points.argtypes = [c_vp, c_vp] + asw_tail + [c_vp, c_vp, c_vp]
+    L.ss_normalize_colormap.argtypes = [c_vp, c_int, c_int, c_vp, c_vp, c_vp]
+    L.ss_normalize_colormap_device.argtypes = [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]
+    L.ss_remap_linear.argtypes = [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp]
+    L.ss_remap_linear_device.argtypes = [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp]
     for s in SYMBOLS:
         if s != "ss_last_error":
             getattr(L, s).restype = c_int

@@ -26,6 +26,7 @@
 // No CPU fallback exists: every entry point fails with SS_ERR_CUDA when no device is usable.
 
 #include "../../include/ss_passive.h"
+#include "../../include/ss_post.h"
 
 #include <cuda_runtime.h>
 
@@ -33,6 +34,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -1234,6 +1236,7 @@ struct Ctx {
     int device = -1;
     cudaStream_t stream = nullptr;
     DevBuf img1, img2, out, f1, f2, evol, vol0, vol1, keysL, keysR, prox, stage_l, stage_r, stage_i, dense;
+    DevBuf post_mm, post_pts, post_a;   // scratch of the pre/post steps (ss_post.cuh)
     // cached proximity table key
     int prox_win = -1;
     double prox_gp = -1;
@@ -1304,7 +1307,7 @@ int ctx_init(int device) {
     if (c.ready && device != c.device) {
         // switching device: drop the cache
         DevBuf *bufs[] = {&c.img1, &c.img2, &c.out, &c.f1, &c.f2, &c.evol, &c.vol0, &c.vol1, &c.keysL, &c.keysR,
-                          &c.prox, &c.stage_l, &c.stage_r, &c.stage_i, &c.dense};
+                          &c.prox, &c.stage_l, &c.stage_r, &c.stage_i, &c.dense, &c.post_mm, &c.post_pts, &c.post_a};
         for (DevBuf *b : bufs) { if (b->p) cudaFree(b->p); *b = DevBuf(); }
         if (c.stream) cudaStreamDestroy(c.stream);
         c.stream = nullptr;
@@ -1711,7 +1714,7 @@ int ss_shutdown(void) {
     if (!c.ready) return SS_OK;
     cudaSetDevice(c.device);
     DevBuf *bufs[] = {&c.img1, &c.img2, &c.out, &c.f1, &c.f2, &c.evol, &c.vol0, &c.vol1, &c.keysL, &c.keysR,
-                      &c.prox, &c.stage_l, &c.stage_r, &c.stage_i, &c.dense};
+                      &c.prox, &c.stage_l, &c.stage_r, &c.stage_i, &c.dense, &c.post_mm, &c.post_pts, &c.post_a};
     for (DevBuf *b : bufs) { if (b->p) cudaFree(b->p); *b = DevBuf(); }
     for (auto &ev : c.events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     c.events.clear();
@@ -1920,3 +1923,5 @@ int ss_debug_get(float *out, int nfloats) {
 #endif
 
 }  // extern "C"
+
+#include "ss_post.cuh"

@@ -1,0 +1,289 @@
+// ss_post.cuh -- the steps either side of the ASW / GSW hot path, part of libsspassive.so.
+// Included at the end of ss_passive.cu (same translation unit: shares the context, the scratch cache and the
+// error plumbing).  Declared in include/ss_post.h.
+//
+//   k_reproject           disparity -> 3-D points, cv2.reprojectImageTo3D as called by points.py:176 and
+//                         _rigs.py:628 (double homogeneous transform, float32 rounding before AND after the
+//                         multiplication by 1/w, exactly OpenCV 4.x).  12 B written per pixel: HBM-write bound.
+//   k_minmax_i16 +
+//   k_normalize_colormap  cv2.normalize(.., 0, 255, NORM_MINMAX, CV_8UC1) + cv2.applyColorMap (examples/010:44-45).
+//   k_remap_linear        cv2.remap(.., INTER_LINEAR), BORDER_CONSTANT 0 (_rigs.py:564-565): 5-bit fixed-point
+//                         coordinates, 15-bit weights, exactly OpenCV's arithmetic.  Gather, HBM/L2 bound.
+//
+// All three are O(W*H) and bit-exact against OpenCV (tests/test_gpu_post.py, oracle/post_oracle.py).
+
+namespace {
+
+struct Q16 {
+    double q[16];
+};
+
+__global__ void k_reproject(const int16_t *__restrict__ disp, float *__restrict__ pts, int W, int H, Q16 Q) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t i = (size_t)y * W + x;
+    const double d = (double)disp[i], xd = (double)x, yd = (double)y;
+    // Q * (x, y, d, 1): row sums left to right, no contraction (OpenCV's Matx44d * Vec4d)
+    auto row = [&](int k) {
+        const double *q = Q.q + 4 * k;
+        return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(q[0], xd), __dmul_rn(q[1], yd)), __dmul_rn(q[2], d)), q[3]);
+    };
+    const double iw = __ddiv_rn(1.0, row(3));                             // Vec3f /= w is *= 1/w in OpenCV
+    float *o = pts + 3 * i;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float X = __double2float_rn(row(k));                        // Vec3f = Vec3d(homogeneous point)
+        o[k] = __double2float_rn(__dmul_rn((double)X, iw));
+    }
+}
+
+// mm[0] = min, mm[1] = max, initialised to INT_MAX / INT_MIN by the caller
+__global__ void k_minmax_i16(const int16_t *__restrict__ disp, long long n, int *__restrict__ mm) {
+    int lo = 32767, hi = -32768;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int v = disp[i];
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mm, lo);
+        atomicMax(mm + 1, hi);
+    }
+}
+
+__global__ void k_normalize_colormap(const int16_t *__restrict__ disp, long long n, const int *__restrict__ mm,
+                                     const uint8_t *__restrict__ lut, uint8_t *__restrict__ gray, uint8_t *__restrict__ bgr) {
+    __shared__ uint8_t slut[768];
+    for (int k = threadIdx.x; k < 768; k += blockDim.x) slut[k] = lut[k];
+    __syncthreads();
+    // cv::normalize: scale = (255 - 0) * (1 / (smax - smin)) or 0, shift = 0 - smin * scale, in double
+    const double smin = (double)mm[0], smax = (double)mm[1];
+    const double range = smax - smin;
+    const double scale = 255.0 * (range > 2.220446049250313e-16 ? 1.0 / range : 0.0);
+    const double shift = 0.0 - smin * scale;
+    const float a = (float)scale, b = (float)shift;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        // convertTo: one rounding (fma), round half to even, saturate to uint8
+        const int r = __float2int_rn(fmaf((float)disp[i], a, b));
+        const int g = min(255, max(0, r));
+        if (gray) gray[i] = (uint8_t)g;
+        if (bgr) {
+            bgr[3 * i + 0] = slut[3 * g + 0];
+            bgr[3 * i + 1] = slut[3 * g + 1];
+            bgr[3 * i + 2] = slut[3 * g + 2];
+        }
+    }
+}
+
+// cvRound(v * 32) the way OpenCV's remap sees it on x86: round half to even; NaN / inf / out of int range -> INT_MIN
+__device__ __forceinline__ int cvround32(float v) {
+    const float f = v * 32.0f;
+    if (!(fabsf(f) < 2147483648.0f)) return (int)0x80000000;
+    return __float2int_rn(f);
+}
+
+__global__ void k_remap_linear(const uint8_t *__restrict__ src, int sw, int sh, const float *__restrict__ mapx,
+                               const float *__restrict__ mapy, int dw, int dh, uint8_t *__restrict__ dst) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= dw || y >= dh) return;
+    const size_t i = (size_t)y * dw + x;
+    const int sx = cvround32(mapx[i]), sy = cvround32(mapy[i]);
+    const int ax = sx & 31, ay = sy & 31;
+    const int ix = min(32767, max(-32768, sx >> 5)), iy = min(32767, max(-32768, sy >> 5));
+    const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
+    int acc[3] = {0, 0, 0};
+    auto tap = [&](int yy, int xx, int w) {
+        if (w == 0 || xx < 0 || xx >= sw || yy < 0 || yy >= sh) return;         // BORDER_CONSTANT, value 0
+        const uint8_t *p = src + 3 * ((size_t)yy * sw + xx);
+        acc[0] += w * p[0];
+        acc[1] += w * p[1];
+        acc[2] += w * p[2];
+    };
+    tap(iy, ix, w00);
+    tap(iy, ix + 1, w01);
+    tap(iy + 1, ix, w10);
+    tap(iy + 1, ix + 1, w11);
+    uint8_t *o = dst + 3 * i;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = (uint8_t)min(255, (acc[c] + (1 << 14)) >> 15);
+}
+
+int post_reproject_enqueue(Ctx &c, const int16_t *d_disp, int W, int H, const double *Q, float *d_pts, cudaStream_t st) {
+    Q16 q;
+    for (int k = 0; k < 16; ++k) q.q[k] = Q[k];
+    dim3 b(256), g((W + 255) / 256, H);
+    k_reproject<<<g, b, 0, st>>>(d_disp, d_pts, W, H, q);
+    CU_TRY(cudaGetLastError());
+    c.total_launches += 1;
+    return SS_OK;
+}
+
+int post_colormap_enqueue(Ctx &c, const int16_t *d_disp, int W, int H, const uint8_t *d_lut, uint8_t *d_gray, uint8_t *d_bgr,
+                          cudaStream_t st) {
+    int rc;
+    if ((rc = ensure(c.post_mm, 2 * sizeof(int)))) return rc;
+    const int init[2] = {2147483647, (int)0x80000000};
+    CU_TRY(cudaMemcpyAsync(c.post_mm.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const long long n = (long long)W * H;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+    k_minmax_i16<<<blocks, 256, 0, st>>>(d_disp, n, (int *)c.post_mm.p);
+    k_normalize_colormap<<<blocks, 256, 0, st>>>(d_disp, n, (const int *)c.post_mm.p, d_lut, d_gray, d_bgr);
+    CU_TRY(cudaGetLastError());
+    c.total_launches += 2;
+    return SS_OK;
+}
+
+int post_check_dims(int W, int H) {
+    if (W <= 0 || H <= 0) return fail(SS_ERR_DIMS, "Wrong image dimensions!");
+    return SS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ss_reproject_device(const int16_t *d_disp, int width, int height, const double *Q, float *d_points, void *stream) {
+    if (!d_disp || !Q || !d_points) return fail(SS_ERR_FORMAT, "Invalid input format!");
+    int rc = post_check_dims(width, height);
+    if (rc) return rc;
+    Ctx &c = g_ctx;
+    std::lock_guard<std::mutex> lk(c.mu);
+    if ((rc = ctx_init(-1))) return rc;
+    return post_reproject_enqueue(c, d_disp, width, height, Q, d_points, (cudaStream_t)stream);
+}
+
+int ss_reproject(const int16_t *disp, int width, int height, const double *Q, float *points) {
+    if (!disp || !Q || !points) return fail(SS_ERR_FORMAT, "Invalid input format!");
+    int rc = post_check_dims(width, height);
+    if (rc) return rc;
+    Ctx &c = g_ctx;
+    std::lock_guard<std::mutex> lk(c.mu);
+    if ((rc = ctx_init(-1))) return rc;
+    CU_TRY(cudaSetDevice(c.device));
+    const size_t n = (size_t)width * height;
+    if ((rc = ensure(c.out, n * 2 + 2))) return rc;
+    if ((rc = ensure(c.post_pts, n * 12))) return rc;
+    cudaStream_t st = c.stream;
+    CU_TRY(cudaMemcpyAsync(c.out.p, disp, n * 2, cudaMemcpyHostToDevice, st));
+    if ((rc = post_reproject_enqueue(c, (const int16_t *)c.out.p, width, height, Q, (float *)c.post_pts.p, st))) return rc;
+    CU_TRY(cudaMemcpyAsync(points, c.post_pts.p, n * 12, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return SS_OK;
+}
+
+int ss_asw_compute_points(const uint8_t *img1, const uint8_t *img2, int width, int height, int win_size, int max_disp,
+                          int min_disp, double gamma_c, double gamma_p, int consistent, const double *Q, int16_t *out_disp,
+                          float *out_points) {
+    if (!img1 || !img2 || !Q || !out_points) return fail(SS_ERR_FORMAT, "Invalid input format!");
+    const Call q = asw_call(width, height, win_size, max_disp, min_disp, gamma_c, gamma_p, consistent, 0, height);
+    int rc = validate(q);
+    if (rc) return rc;
+    Ctx &c = g_ctx;
+    std::lock_guard<std::mutex> lk(c.mu);
+    if ((rc = ctx_init(-1))) return rc;
+    CU_TRY(cudaSetDevice(c.device));
+    const size_t nimg = (size_t)width * height * 3, npx = (size_t)width * height;
+    if ((rc = ensure(c.img1, nimg))) return rc;
+    if ((rc = ensure(c.img2, nimg))) return rc;
+    if ((rc = ensure(c.out, npx * 2 + 2))) return rc;
+    if ((rc = ensure(c.post_pts, npx * 12))) return rc;
+    cudaStream_t st = c.stream;
+    CU_TRY(cudaMemcpyAsync(c.img1.p, img1, nimg, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(c.img2.p, img2, nimg, cudaMemcpyHostToDevice, st));
+    Outputs o;
+    o.d_final = (int16_t *)c.out.p;
+    if ((rc = run_device(c, q, (const uint8_t *)c.img1.p, (const uint8_t *)c.img2.p, o, st))) return rc;
+    // the disparity map never leaves the device between the WTA tail and the reprojection
+    if ((rc = post_reproject_enqueue(c, (const int16_t *)c.out.p, width, height, Q, (float *)c.post_pts.p, st))) return rc;
+    if (out_disp) CU_TRY(cudaMemcpyAsync(out_disp, c.out.p, npx * 2, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(out_points, c.post_pts.p, npx * 12, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return SS_OK;
+}
+
+int ss_normalize_colormap_device(const int16_t *d_disp, int width, int height, const uint8_t *d_lut_bgr, uint8_t *d_gray,
+                                 uint8_t *d_bgr, void *stream) {
+    if (!d_disp || !d_lut_bgr || (!d_gray && !d_bgr)) return fail(SS_ERR_FORMAT, "Invalid input format!");
+    int rc = post_check_dims(width, height);
+    if (rc) return rc;
+    Ctx &c = g_ctx;
+    std::lock_guard<std::mutex> lk(c.mu);
+    if ((rc = ctx_init(-1))) return rc;
+    return post_colormap_enqueue(c, d_disp, width, height, d_lut_bgr, d_gray, d_bgr, (cudaStream_t)stream);
+}
+
+int ss_normalize_colormap(const int16_t *disp, int width, int height, const uint8_t *lut_bgr, uint8_t *gray, uint8_t *bgr) {
+    if (!disp || !lut_bgr || (!gray && !bgr)) return fail(SS_ERR_FORMAT, "Invalid input format!");
+    int rc = post_check_dims(width, height);
+    if (rc) return rc;
+    Ctx &c = g_ctx;
+    std::lock_guard<std::mutex> lk(c.mu);
+    if ((rc = ctx_init(-1))) return rc;
+    CU_TRY(cudaSetDevice(c.device));
+    const size_t n = (size_t)width * height;
+    if ((rc = ensure(c.out, n * 2 + 2))) return rc;
+    if ((rc = ensure(c.post_a, n * 4 + 768))) return rc;          // [lut 768 | gray n | bgr 3n]
+    cudaStream_t st = c.stream;
+    uint8_t *d_lut = (uint8_t *)c.post_a.p, *d_gray = d_lut + 768, *d_bgr = d_gray + n;
+    CU_TRY(cudaMemcpyAsync(c.out.p, disp, n * 2, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_lut, lut_bgr, 768, cudaMemcpyHostToDevice, st));
+    if ((rc = post_colormap_enqueue(c, (const int16_t *)c.out.p, width, height, d_lut, d_gray, d_bgr, st))) return rc;
+    if (gray) CU_TRY(cudaMemcpyAsync(gray, d_gray, n, cudaMemcpyDeviceToHost, st));
+    if (bgr) CU_TRY(cudaMemcpyAsync(bgr, d_bgr, 3 * n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return SS_OK;
+}
+
+int ss_remap_linear_device(const uint8_t *d_src, int src_width, int src_height, const float *d_mapx, const float *d_mapy,
+                           int dst_width, int dst_height, uint8_t *d_dst, void *stream) {
+    if (!d_src || !d_mapx || !d_mapy || !d_dst) return fail(SS_ERR_FORMAT, "Invalid input format!");
+    int rc = post_check_dims(src_width, src_height);
+    if (rc) return rc;
+    if ((rc = post_check_dims(dst_width, dst_height))) return rc;
+    Ctx &c = g_ctx;
+    std::lock_guard<std::mutex> lk(c.mu);
+    if ((rc = ctx_init(-1))) return rc;
+    dim3 b(128), g((dst_width + 127) / 128, dst_height);
+    k_remap_linear<<<g, b, 0, (cudaStream_t)stream>>>(d_src, src_width, src_height, d_mapx, d_mapy, dst_width, dst_height, d_dst);
+    CU_TRY(cudaGetLastError());
+    c.total_launches += 1;
+    return SS_OK;
+}
+
+int ss_remap_linear(const uint8_t *src, int src_width, int src_height, const float *mapx, const float *mapy, int dst_width,
+                    int dst_height, uint8_t *dst) {
+    if (!src || !mapx || !mapy || !dst) return fail(SS_ERR_FORMAT, "Invalid input format!");
+    int rc = post_check_dims(src_width, src_height);
+    if (rc) return rc;
+    if ((rc = post_check_dims(dst_width, dst_height))) return rc;
+    Ctx &c = g_ctx;
+    std::lock_guard<std::mutex> lk(c.mu);
+    if ((rc = ctx_init(-1))) return rc;
+    CU_TRY(cudaSetDevice(c.device));
+    const size_t ns = (size_t)src_width * src_height * 3, nd = (size_t)dst_width * dst_height;
+    if ((rc = ensure(c.img1, ns))) return rc;
+    if ((rc = ensure(c.post_pts, nd * 8))) return rc;             // mapx | mapy
+    if ((rc = ensure(c.post_a, nd * 3))) return rc;
+    cudaStream_t st = c.stream;
+    float *d_mx = (float *)c.post_pts.p, *d_my = d_mx + nd;
+    CU_TRY(cudaMemcpyAsync(c.img1.p, src, ns, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_mx, mapx, nd * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_my, mapy, nd * 4, cudaMemcpyHostToDevice, st));
+    dim3 b(128), g((dst_width + 127) / 128, dst_height);
+    k_remap_linear<<<g, b, 0, st>>>((const uint8_t *)c.img1.p, src_width, src_height, d_mx, d_my, dst_width, dst_height,
+                                    (uint8_t *)c.post_a.p);
+    CU_TRY(cudaGetLastError());
+    c.total_launches += 1;
+    CU_TRY(cudaMemcpyAsync(dst, c.post_a.p, nd * 3, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return SS_OK;
+}
+
+}  // extern "C"

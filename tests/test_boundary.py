@@ -22,7 +22,7 @@ def _cuda():
 
 
 def test_header_symbols_are_exported():
-    hdr = open(os.path.join(ROOT, "include", "ss_passive.h")).read()
+    hdr = open(os.path.join(ROOT, "include", "ss_passive.h")).read() + open(os.path.join(ROOT, "include", "ss_post.h")).read()
     declared = set(re.findall(r"\b(ss_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
     lib = ctypes.CDLL(_cabi.LIB_PATH)
@@ -66,6 +66,28 @@ def test_no_cpu_fallback():
     a = np.zeros((8, 9, 3), np.uint8)
     with pytest.raises(RuntimeError, match="no usable CUDA device"):
         ss.passive.StereoASW(winSize=3, maxDisparity=2).compute(a, a)
+    d = np.zeros((8, 9), np.int16)
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        ss.points.getAdimensional3DPoints(d)
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        ss.display.applyColorMap(d)
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        ss.rectify.remap(a, np.zeros((4, 5), np.float32), np.zeros((4, 5), np.float32))
+
+
+def test_post_path_validation_without_gpu():
+    d = np.zeros((8, 9), np.int16)
+    with pytest.raises(TypeError, match="Wrong type input!"):
+        ss.points.getAdimensional3DPoints(d.astype(np.float32))
+    with pytest.raises(ValueError):
+        ss.points.reprojectImageTo3D(d, np.eye(3))
+    with pytest.raises(ValueError, match="Wrong image dimensions!"):
+        ss.display.applyColorMap(np.zeros((2, 3, 3), np.int16))
+    with pytest.raises(TypeError, match="Wrong type input!"):
+        ss.rectify.remap(np.zeros((8, 9, 3), np.float32), np.zeros((4, 5), np.float32), np.zeros((4, 5), np.float32))
+    # the Q of points.getAdimensional3DPoints (points.py:147-174)
+    Q = ss.points.buildQ(b=1, fx=384, fy=384, cx1=192, cx2=192, a1=0, a2=0, cy=144)
+    assert np.array_equal(Q, np.array([[1, 0, 0, -192.0], [0, 1, 0, -144.0], [0, 0, 0, -384.0], [0, 0, 1.0, 0]]))
 
 
 def test_product_never_imports_oracle():
