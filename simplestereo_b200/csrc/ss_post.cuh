@@ -18,19 +18,14 @@ struct Q16 {
     double q[16];
 };
 
-__global__ void k_reproject(const int16_t *__restrict__ disp, float *__restrict__ pts, int W, int H, Q16 Q) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    if (x >= W || y >= H) return;
-    const size_t i = (size_t)y * W + x;
-    const double d = (double)disp[i], xd = (double)x, yd = (double)y;
+__device__ __forceinline__ void reproject_px(const Q16 &Q, int x, int y, int disp, float *o) {
+    const double d = (double)disp, xd = (double)x, yd = (double)y;
     // Q * (x, y, d, 1): row sums left to right, no contraction (OpenCV's Matx44d * Vec4d)
     auto row = [&](int k) {
         const double *q = Q.q + 4 * k;
         return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(q[0], xd), __dmul_rn(q[1], yd)), __dmul_rn(q[2], d)), q[3]);
     };
     const double iw = __ddiv_rn(1.0, row(3));                             // Vec3f /= w is *= 1/w in OpenCV
-    float *o = pts + 3 * i;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float X = __double2float_rn(row(k));                        // Vec3f = Vec3d(homogeneous point)
@@ -38,10 +33,39 @@ __global__ void k_reproject(const int16_t *__restrict__ disp, float *__restrict_
     }
 }
 
-// mm[0] = min, mm[1] = max, initialised to INT_MAX / INT_MIN by the caller
-__global__ void k_minmax_i16(const int16_t *__restrict__ disp, long long n, int *__restrict__ mm) {
+// VEC = 4: four pixels per thread, one 8-byte load and three 16-byte stores (needs W % 4 == 0)
+template <int VEC>
+__global__ void k_reproject(const int16_t *__restrict__ disp, float *__restrict__ pts, int W, int H, Q16 Q) {
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    const int y = blockIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t i = (size_t)y * W + x;
+    if (VEC == 4) {
+        const short4 d4 = *reinterpret_cast<const short4 *>(disp + i);
+        float o[12];
+        reproject_px(Q, x, y, d4.x, o);
+        reproject_px(Q, x + 1, y, d4.y, o + 3);
+        reproject_px(Q, x + 2, y, d4.z, o + 6);
+        reproject_px(Q, x + 3, y, d4.w, o + 9);
+        float4 *dst = reinterpret_cast<float4 *>(pts + 3 * i);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+    } else {
+        reproject_px(Q, x, y, disp[i], pts + 3 * i);
+    }
+}
+
+// mm[0] = min(v), mm[1] = min(-v): both start at 0x7f7f7f7f (one cudaMemsetAsync), max = -mm[1]
+__global__ void k_minmax_i16(const int16_t *__restrict__ disp, long long n, int *__restrict__ mm, int vec4) {
     int lo = 32767, hi = -32768;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long n4 = vec4 ? n / 4 : 0;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
+        const short4 d4 = *reinterpret_cast<const short4 *>(disp + 4 * q);
+        lo = min(min(lo, (int)d4.x), min(min((int)d4.y, (int)d4.z), (int)d4.w));
+        hi = max(max(hi, (int)d4.x), max(max((int)d4.y, (int)d4.z), (int)d4.w));
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int v = disp[i];
         lo = min(lo, v);
         hi = max(hi, v);
@@ -51,32 +75,54 @@ __global__ void k_minmax_i16(const int16_t *__restrict__ disp, long long n, int 
         lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
         hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    if ((threadIdx.x & 31) == 0) {
+    // one pair of global atomics per block: same-address atomics serialise in L2
+    __shared__ int s_lo[32], s_hi[32];
+    const int wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0) { s_lo[wid] = lo; s_hi[wid] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < nw; ++k) { lo = min(lo, s_lo[k]); hi = max(hi, s_hi[k]); }
         atomicMin(mm, lo);
-        atomicMax(mm + 1, hi);
+        atomicMin(mm + 1, -hi);
     }
 }
 
 __global__ void k_normalize_colormap(const int16_t *__restrict__ disp, long long n, const int *__restrict__ mm,
-                                     const uint8_t *__restrict__ lut, uint8_t *__restrict__ gray, uint8_t *__restrict__ bgr) {
-    __shared__ uint8_t slut[768];
-    for (int k = threadIdx.x; k < 768; k += blockDim.x) slut[k] = lut[k];
+                                     const uint8_t *__restrict__ lut, uint8_t *__restrict__ gray, uint8_t *__restrict__ bgr,
+                                     int vec4) {
+    __shared__ uint32_t slut[256];                                 // B | G << 8 | R << 16 per level
+    for (int k = threadIdx.x; k < 256; k += blockDim.x)
+        slut[k] = (uint32_t)lut[3 * k] | ((uint32_t)lut[3 * k + 1] << 8) | ((uint32_t)lut[3 * k + 2] << 16);
     __syncthreads();
     // cv::normalize: scale = (255 - 0) * (1 / (smax - smin)) or 0, shift = 0 - smin * scale, in double
-    const double smin = (double)mm[0], smax = (double)mm[1];
+    const double smin = (double)mm[0], smax = -(double)mm[1];
     const double range = smax - smin;
     const double scale = 255.0 * (range > 2.220446049250313e-16 ? 1.0 / range : 0.0);
     const double shift = 0.0 - smin * scale;
     const float a = (float)scale, b = (float)shift;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        // convertTo: one rounding (fma), round half to even, saturate to uint8
-        const int r = __float2int_rn(fmaf((float)disp[i], a, b));
-        const int g = min(255, max(0, r));
+    // convertTo: one rounding (fma), round half to even, saturate to uint8
+    auto level = [&](int v) { return min(255, max(0, __float2int_rn(fmaf((float)v, a, b)))); };
+    const long long n4 = vec4 ? n / 4 : 0;                     // groups of 4 pixels: 8-byte load, 4 + 12-byte stores
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
+        const short4 d4 = *reinterpret_cast<const short4 *>(disp + 4 * q);
+        const int g0 = level(d4.x), g1 = level(d4.y), g2 = level(d4.z), g3 = level(d4.w);
+        if (gray) *reinterpret_cast<uint32_t *>(gray + 4 * q) = (uint32_t)g0 | ((uint32_t)g1 << 8) | ((uint32_t)g2 << 16) | ((uint32_t)g3 << 24);
+        if (bgr) {
+            const uint32_t c0 = slut[g0], c1 = slut[g1], c2 = slut[g2], c3 = slut[g3];
+            uint32_t *o = reinterpret_cast<uint32_t *>(bgr + 12 * q);
+            o[0] = c0 | (c1 << 24);
+            o[1] = (c1 >> 8) | (c2 << 16);
+            o[2] = (c2 >> 16) | (c3 << 8);
+        }
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int g = level(disp[i]);
         if (gray) gray[i] = (uint8_t)g;
         if (bgr) {
-            bgr[3 * i + 0] = slut[3 * g + 0];
-            bgr[3 * i + 1] = slut[3 * g + 1];
-            bgr[3 * i + 2] = slut[3 * g + 2];
+            const uint32_t cc = slut[g];
+            bgr[3 * i + 0] = (uint8_t)cc;
+            bgr[3 * i + 1] = (uint8_t)(cc >> 8);
+            bgr[3 * i + 2] = (uint8_t)(cc >> 16);
         }
     }
 }
@@ -118,8 +164,14 @@ __global__ void k_remap_linear(const uint8_t *__restrict__ src, int sw, int sh, 
 int post_reproject_enqueue(Ctx &c, const int16_t *d_disp, int W, int H, const double *Q, float *d_pts, cudaStream_t st) {
     Q16 q;
     for (int k = 0; k < 16; ++k) q.q[k] = Q[k];
-    dim3 b(256), g((W + 255) / 256, H);
-    k_reproject<<<g, b, 0, st>>>(d_disp, d_pts, W, H, q);
+    const bool vec = (W % 4 == 0) && ((uintptr_t)d_disp % 8 == 0) && ((uintptr_t)d_pts % 16 == 0);
+    if (vec) {
+        dim3 b(128), g((W / 4 + 127) / 128, H);
+        k_reproject<4><<<g, b, 0, st>>>(d_disp, d_pts, W, H, q);
+    } else {
+        dim3 b(256), g((W + 255) / 256, H);
+        k_reproject<1><<<g, b, 0, st>>>(d_disp, d_pts, W, H, q);
+    }
     CU_TRY(cudaGetLastError());
     c.total_launches += 1;
     return SS_OK;
@@ -129,12 +181,12 @@ int post_colormap_enqueue(Ctx &c, const int16_t *d_disp, int W, int H, const uin
                           cudaStream_t st) {
     int rc;
     if ((rc = ensure(c.post_mm, 2 * sizeof(int)))) return rc;
-    const int init[2] = {2147483647, (int)0x80000000};
-    CU_TRY(cudaMemcpyAsync(c.post_mm.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(c.post_mm.p, 0x7f, 2 * sizeof(int), st));
     const long long n = (long long)W * H;
-    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
-    k_minmax_i16<<<blocks, 256, 0, st>>>(d_disp, n, (int *)c.post_mm.p);
-    k_normalize_colormap<<<blocks, 256, 0, st>>>(d_disp, n, (const int *)c.post_mm.p, d_lut, d_gray, d_bgr);
+    const int vec4 = ((uintptr_t)d_disp % 8 == 0) && (!d_gray || (uintptr_t)d_gray % 4 == 0) && (!d_bgr || (uintptr_t)d_bgr % 4 == 0);
+    const int blocks = (int)std::min<long long>((n / 4 + 255) / 256 + 1, 148 * 16);
+    k_minmax_i16<<<blocks, 256, 0, st>>>(d_disp, n, (int *)c.post_mm.p, vec4);
+    k_normalize_colormap<<<blocks, 256, 0, st>>>(d_disp, n, (const int *)c.post_mm.p, d_lut, d_gray, d_bgr, vec4);
     CU_TRY(cudaGetLastError());
     c.total_launches += 2;
     return SS_OK;
@@ -229,9 +281,9 @@ int ss_normalize_colormap(const int16_t *disp, int width, int height, const uint
     CU_TRY(cudaSetDevice(c.device));
     const size_t n = (size_t)width * height;
     if ((rc = ensure(c.out, n * 2 + 2))) return rc;
-    if ((rc = ensure(c.post_a, n * 4 + 768))) return rc;          // [lut 768 | gray n | bgr 3n]
+    if ((rc = ensure(c.post_a, n * 4 + 768 + 8))) return rc;      // [lut 768 | bgr 3n, padded to 4 | gray n]
     cudaStream_t st = c.stream;
-    uint8_t *d_lut = (uint8_t *)c.post_a.p, *d_gray = d_lut + 768, *d_bgr = d_gray + n;
+    uint8_t *d_lut = (uint8_t *)c.post_a.p, *d_bgr = d_lut + 768, *d_gray = d_bgr + ((3 * n + 3) & ~(size_t)3);
     CU_TRY(cudaMemcpyAsync(c.out.p, disp, n * 2, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_lut, lut_bgr, 768, cudaMemcpyHostToDevice, st));
     if ((rc = post_colormap_enqueue(c, (const int16_t *)c.out.p, width, height, d_lut, d_gray, d_bgr, st))) return rc;
