@@ -52,6 +52,16 @@ int ss_remap_linear(const uint8_t *src, int src_width, int src_height, const flo
 int ss_remap_linear_device(const uint8_t *d_src, int src_width, int src_height, const float *d_mapx,
                            const float *d_mapy, int dst_width, int dst_height, uint8_t *d_dst, void *stream);
 
+/* ---- point-cloud export ------------------------------------------------------------------- */
+
+/* simplestereo.points.exportPLY(points3D, filepath, referenceImage=None, precision=6) -- simplestereo/points.py:10-80.
+ * Host-side ASCII writer, byte-identical to the reference's per-point Python loop, formatted on all host threads.
+ * points: n x 3 float32 (points_are_double == 0) or float64; shape / ndims: the original array shape for the header
+ * comment; bgr: optional n x 3 uint8 (written as R G B); intensity: optional n values, int64 (intensity_kind 1) or
+ * float64 (2), used only when bgr is NULL. */
+int ss_export_ply(const void *points, int points_are_double, long long n, const long long *shape, int ndims,
+                  const uint8_t *bgr, const void *intensity, int intensity_kind, const char *path, int precision);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,7 @@ SYMBOLS = (
     # include/ss_post.h
     "ss_reproject", "ss_reproject_device", "ss_asw_compute_points",
     "ss_normalize_colormap", "ss_normalize_colormap_device", "ss_remap_linear", "ss_remap_linear_device",
+    "ss_export_ply",
 )
 
 _lib = None
@@ -78,6 +79,7 @@ def lib():
     L.ss_normalize_colormap_device.argtypes = [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]
     L.ss_remap_linear.argtypes = [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp]
     L.ss_remap_linear_device.argtypes = [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp]
+    L.ss_export_ply.argtypes = [c_vp, c_int, c_ll, c_vp, c_int, c_vp, c_vp, c_int, ctypes.c_char_p, c_int]
     for s in SYMBOLS:
         if s != "ss_last_error":
             getattr(L, s).restype = c_int

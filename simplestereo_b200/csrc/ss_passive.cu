@@ -37,6 +37,7 @@
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 

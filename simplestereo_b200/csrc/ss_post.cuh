@@ -339,3 +339,85 @@ int ss_remap_linear(const uint8_t *src, int src_width, int src_height, const flo
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// ss_export_ply -- ASCII PLY writer, byte-identical to simplestereo.points.exportPLY (points.py:10-80), which
+// formats every point in a Python loop (seconds per 4K frame).  Host code: the points come back from the device
+// as float32 [n][3]; formatting is split over the host threads, the file is written in order.
+// ------------------------------------------------------------------------------------------
+
+namespace {
+
+// Python's "{:.{p}f}".format(v): correctly rounded like glibc's printf, but nan never carries a sign
+inline void ply_fmt(std::string &o, double v, int precision, int width) {
+    char buf[400];
+    if (std::isnan(v)) {
+        snprintf(buf, sizeof(buf), "%*s", width, "nan");
+    } else if (width >= 0) {
+        snprintf(buf, sizeof(buf), "%*f", width, v);               // "{:{p}f}": width p, default precision 6 (points.py:77)
+    } else {
+        snprintf(buf, sizeof(buf), "%.*f", precision, v);
+    }
+    o += buf;
+}
+
+}  // namespace
+
+extern "C" int ss_export_ply(const void *points, int points_are_double, long long n, const long long *shape, int ndims,
+                             const uint8_t *bgr, const void *intensity, int intensity_kind, const char *path,
+                             int precision) {
+    if (!points || !path || n < 0 || ndims < 0 || (ndims > 0 && !shape) || precision < 0 || precision > 300)
+        return fail(SS_ERR_FORMAT, "Invalid input format!");
+    if (intensity && intensity_kind != 1 && intensity_kind != 2) return fail(SS_ERR_FORMAT, "Invalid input format!");
+    FILE *f = fopen(path, "w");
+    if (!f) return fail(SS_ERR_PARAM, std::string("cannot open ") + path + " for writing");
+    std::string hdr = "ply\nformat ascii 1.0\ncomment SimpleStereo point cloud export\ncomment Original array shape ";
+    for (int k = 0; k < ndims; ++k) hdr += (k ? "x" : "") + std::to_string(shape[k]);
+    hdr += "\nelement vertex " + std::to_string(n) + "\nproperty double x\nproperty double y\nproperty double z\n";
+    if (bgr) hdr += "property uchar red\nproperty uchar green\nproperty uchar blue\n";
+    else if (intensity) hdr += intensity_kind == 1 ? "property int intensity\n" : "property float intensity\n";
+    hdr += "end_header\n";
+    fwrite(hdr.data(), 1, hdr.size(), f);
+
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const long long per = 1 << 16;                                 // points per work item
+    const long long nitems = (n + per - 1) / per;
+    const unsigned nthreads = (unsigned)std::min<long long>(hw, std::max<long long>(nitems, 1));
+    bool ok = true;
+    for (long long base = 0; base < nitems && ok; base += nthreads) {
+        const unsigned cnt = (unsigned)std::min<long long>(nthreads, nitems - base);
+        std::vector<std::string> out(cnt);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < cnt; ++t) {
+            th.emplace_back([&, t]() {
+                const long long i0 = (base + t) * per, i1 = std::min(n, i0 + per);
+                std::string &o = out[t];
+                o.reserve((size_t)(i1 - i0) * (3 * (precision + 8) + 16));
+                for (long long i = i0; i < i1; ++i) {
+                    for (int k = 0; k < 3; ++k) {
+                        const double v = points_are_double ? static_cast<const double *>(points)[3 * i + k]
+                                                           : (double)static_cast<const float *>(points)[3 * i + k];
+                        if (k) o += ' ';
+                        ply_fmt(o, v, precision, -1);
+                    }
+                    if (bgr) {                                     // BGR -> RGB (points.py:55)
+                        o += ' '; o += std::to_string((int)bgr[3 * i + 2]);
+                        o += ' '; o += std::to_string((int)bgr[3 * i + 1]);
+                        o += ' '; o += std::to_string((int)bgr[3 * i + 0]);
+                    } else if (intensity && intensity_kind == 1) {
+                        o += ' '; o += std::to_string(static_cast<const long long *>(intensity)[i]);
+                    } else if (intensity) {
+                        o += ' ';
+                        ply_fmt(o, static_cast<const double *>(intensity)[i], 6, precision);
+                    }
+                    o += '\n';
+                }
+            });
+        }
+        for (auto &x : th) x.join();
+        for (unsigned t = 0; t < cnt && ok; ++t) ok = fwrite(out[t].data(), 1, out[t].size(), f) == out[t].size();
+    }
+    if (fclose(f) != 0) ok = false;
+    if (!ok) return fail(SS_ERR_PARAM, std::string("short write to ") + path);
+    return SS_OK;
+}

@@ -85,3 +85,71 @@ def computePoints(matcher, img1, img2, Q, return_disparity=False):
     _cabi.check(_cabi.lib().ss_asw_compute_points(_cabi.ptr(img1), _cabi.ptr(img2), w, h, *matcher._args(), _cabi.ptr(Q),
                                                   _cabi.ptr(disp), _cabi.ptr(pts)))
     return (pts, disp) if return_disparity else pts
+
+
+def exportPLY(points3D, filepath, referenceImage=None, precision=6):
+    """
+    Export raw point cloud to PLY file (ASCII) -- reference: simplestereo/points.py:10-80, byte-identical output.
+
+    The reference formats every point in a Python loop; here the text is produced by the native writer
+    ``ss_export_ply`` on all host threads.
+
+    Parameters
+    ----------
+    points3D : numpy.ndarray
+        Array of 3D points. The last dimension must contain ordered x,y,z coordinates.
+    filepath : str
+        File path for the PLY file (absolute or relative).
+    referenceImage : numpy.ndarray, optional
+        Reference image to extract color from: same number of points as `points3D`, last dimension either
+        1 (grayscale) or 3 (BGR, uint8).
+    precision : int
+        Decimal places to save coordinates with. Default to 6.
+    """
+    import ctypes
+    import os
+    points3D = np.asarray(points3D)
+    shape = np.asarray(points3D.shape, dtype=np.int64)
+    pts = points3D.reshape(-1, 3)
+    if pts.dtype == np.float32:
+        is_double = 0
+    else:
+        pts = pts.astype(np.float64, copy=False)
+        is_double = 1
+    pts = np.ascontiguousarray(pts)
+    n = pts.shape[0]
+    bgr = inten = None
+    kind = 0
+    if referenceImage is not None:
+        referenceImage = np.asarray(referenceImage)
+        if referenceImage.size == points3D.size:
+            if referenceImage.dtype != np.uint8:
+                raise TypeError("Wrong type input!")                # "property uchar": BGR images are uint8
+            bgr = np.ascontiguousarray(referenceImage.reshape(-1, 3))
+        else:
+            inten = np.ravel(referenceImage)
+            if inten.size != n:
+                raise ValueError("Wrong image dimensions!")
+            if np.issubdtype(inten.dtype, np.int64):                 # points.py:62
+                inten, kind = np.ascontiguousarray(inten, dtype=np.int64), 1
+            else:
+                inten, kind = np.ascontiguousarray(inten, dtype=np.float64), 2
+    _cabi.check(_cabi.lib().ss_export_ply(_cabi.ptr(pts), is_double, n, _cabi.ptr(shape), int(shape.size), _cabi.ptr(bgr),
+                                          _cabi.ptr(inten), kind, ctypes.c_char_p(os.fsencode(filepath)), int(precision)))
+
+
+def importPLY(filename, *properties):
+    """
+    Import 3D coordinates from PLY file (reference: simplestereo/points.py:82-121).
+
+    ``properties``: property column positions to be extracted as float, in the same order (default (0, 1, 2)).
+    Returns an array of shape (number of values, number of properties).
+    """
+    if not properties:
+        properties = (0, 1, 2)
+    with open(filename, "r") as f:
+        for line in f:
+            if line.rstrip().lower() == "end_header":
+                break
+        rows = [line.split(" ") for line in f]
+    return np.asarray([[float(r[x]) for x in properties] for r in rows], dtype=float)
