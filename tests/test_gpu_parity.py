@@ -330,3 +330,26 @@ def test_c5_full_size_4k_disparity_shards_equal_unsharded():
     parity.adjudicate_left(want[rows[0]:rows[1]], ref["left"][rows[0]:rows[1]], ref["cost"], 0)
     assert (want == gt).mean() > 0.80
     assert want.min() >= 0 and want.max() <= 511
+
+
+def test_gsw_large_window_falls_back_to_single_role_kernel(monkeypatch):
+    """win 51 at DC 128: the float raw-cost tiles do not fit the double-buffered staging of k_aggregate_ws, the call is
+    served by the single-role k_aggregate (exact expf / IEEE sqrt weights).  Same parity bar; and the two kernels agree
+    with each other on a window both can run."""
+    l, r, _ = synth_pair(200, 20, 100, 12)
+    kw = dict(winSize=51, maxDisparity=100, minDisparity=0, gamma=10, fMax=120, iterations=3, bins=20)
+    gpu = ss.passive.StereoGSW(**kw).compute_staged(l, r, cost=True)
+    ref = oracle.gsw(l, r, stages=True, cost=True, **kw)
+    parity.check_cost(gpu["cost_left"], ref["cost_left"], "cost_left")
+    parity.check_cost(gpu["cost_right"], ref["cost_right"], "cost_right")
+    parity.check_staged(gpu, ref, ref["cost_left"], ref["cost_right"], 0, True, max_fraction=0.01, saturation=None)
+    kw["winSize"] = 21
+    ws = ss.passive.StereoGSW(**kw).compute_staged(l, r, cost=True)
+    monkeypatch.setenv("SS_GSW_SINGLE", "1")
+    single = ss.passive.StereoGSW(**kw).compute_staged(l, r, cost=True)
+    monkeypatch.delenv("SS_GSW_SINGLE")
+    fin = np.isfinite(single["cost_left"])
+    assert np.array_equal(fin, np.isfinite(ws["cost_left"]))
+    assert np.allclose(ws["cost_left"][fin], single["cost_left"][fin], rtol=2e-5, atol=1e-5)
+    assert np.allclose(ws["cost_right"][fin], single["cost_right"][fin], rtol=2e-5, atol=1e-5)
+    assert (ws["final"] != single["final"]).mean() < 0.01
