@@ -55,6 +55,9 @@ typedef unsigned long long u64;
 #ifndef SS_SHEAR
 #define SS_SHEAR 1
 #endif
+#ifndef SS_SCALAR_ODD
+#define SS_SCALAR_ODD 1
+#endif
 #ifndef SS_UNROLL
 #define SS_UNROLL 2            // periods (8 window columns) per trip of the consumer loop: 1, 2 or 4
 #endif
@@ -981,6 +984,7 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
                 // right-weight pairs (v[k], v[k+1]): even k are the register pairs the loads produced; odd k either
                 // come from the shifted copy (DUAL) or straddle two loads and cost two moves each
                 const u64 VA[6] = {pk(v0.x, v0.y), pk(v0.z, v0.w), pk(v1.x, v1.y), pk(v1.z, v1.w), pk(v2.x, v2.y), pk(v2.z, v2.w)};
+                const float vf[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
                 u64 VM[5];
                 if (DUAL) {
                     const float *w2b = reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(w2p) + w2copy);
@@ -999,11 +1003,23 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
                         const int k = 7 - a + 2 * bp;                   // reversed right index of disparity kb+2bp
                         const u64 w2d = (k & 1) ? VM[k >> 1] : VA[k >> 1];
                         const u64 e2 = ring[(a + s) & 7][bp];
+                        // SS_SCALAR_ODD: an odd-k pair (v[k], v[k+1]) straddles two loaded register pairs and costs two
+                        // moves before a packed op can read it.  Two scalar ops (1 issue cycle each, same rounding) write
+                        // the halves of an aligned pair directly: 2 cycles instead of 2 (packed) + 2 (moves).
                         if (GSW) {
                             acc0[a][bp] = fma2(w1d, e2, acc0[a][bp]);   // left-reference cost  (_passive.cpp:528)
-                            acc1[a][bp] = fma2(w2d, e2, acc1[a][bp]);   // right-reference cost (:644)
+                            if (SS_SCALAR_ODD && !DUAL && (k & 1)) {    // right-reference cost (:644)
+                                float elo, ehi, alo, ahi;
+                                upk(e2, elo, ehi);
+                                upk(acc1[a][bp], alo, ahi);
+                                acc1[a][bp] = pk(__fmaf_rn(vf[k], elo, alo), __fmaf_rn(vf[k + 1], ehi, ahi));
+                            } else {
+                                acc1[a][bp] = fma2(w2d, e2, acc1[a][bp]);
+                            }
                         } else {
-                            const u64 ww = mul2(w1d, w2d);              // w1*w2
+                            const u64 ww = (SS_SCALAR_ODD && !DUAL && (k & 1))
+                                               ? pk(__fmul_rn(w1[a], vf[k]), __fmul_rn(w1[a], vf[k + 1]))
+                                               : mul2(w1d, w2d);        // w1*w2
                             acc0[a][bp] = fma2(ww, e2, acc0[a][bp]);    // cost += w1*w2*e  (_passive.cpp:77)
                             acc1[a][bp] = add2(acc1[a][bp], ww);        // tot  += w1*w2    (:82)
                         }
