@@ -16,7 +16,7 @@
 //                     tabulates both support-weight rows once per (pixel, offset) -- the reference
 //                     re-evaluates exp/sqrt/pow for every (x,d) pair, _passive.cpp:71-74 -- and
 //                     accumulates numerator / denominator in registers with packed fma.rn.f32x2
-//                     (FFMA2/FMUL2/FADD2: scalar FMUL/FADD are half rate on sm_100).
+//                     (FFMA2/FMUL2/FADD2: two lanes' worth of work per issued instruction).
 //                     WTA over the disparity chunk is fused (warp shuffle + 64-bit atomicMin keys).
 //   k_wta_right       right-reference WTA: minimum over diagonals of the SAME aggregated volume
 //                     (C_R[xr,d] == C_L[xr+d,d]), so the "roughly doubled" second
