@@ -370,7 +370,7 @@ __host__ __device__ inline SmemPlan smem_plan(int win, int DC) {
 template <bool GSW, int DC, int REM>
 __global__ void __launch_bounds__(AggCfg<DC>::NT, AggCfg<DC>::MINB) k_aggregate(const AggParams P) {
     typedef AggCfg<DC> C;
-    constexpr int T = TILE_X, NRp = C::NRp, NT = C::NT;
+    constexpr int T = TILE_X, NRp = C::NRp;
     extern __shared__ __align__(128) unsigned char smem[];
 
     const Geom &g = P.g;
@@ -514,11 +514,11 @@ __global__ void __launch_bounds__(AggCfg<DC>::NT, AggCfg<DC>::MINB) k_aggregate(
 #ifdef SS_DEBUG_DUMP
         if (P.dbg && blockIdx.x == (unsigned)P.dbg[0] && blockIdx.y == (unsigned)P.dbg[1] && blockIdx.z == 0 && n == (int)P.dbg[2]) {
             float *o = P.dbg + 16;
-            for (int k = tid; k < win * T; k += NT) o[k] = W1s[k];
+            for (int k = tid; k < win * T; k += C::NT) o[k] = W1s[k];
             o += win * T;
-            for (int k = tid; k < win * NRp; k += NT) o[k] = W2s[k];
+            for (int k = tid; k < win * NRp; k += C::NT) o[k] = W2s[k];
             o += win * NRp;
-            for (int k = tid; k < NU * DC; k += NT) o[k] = Es[k];
+            for (int k = tid; k < NU * DC; k += C::NT) o[k] = Es[k];
         }
 #endif
 
@@ -1360,6 +1360,8 @@ struct Call {
 int validate(const Call &q) {
     if (q.W <= 0 || q.H <= 0) return fail(SS_ERR_DIMS, "Wrong image dimensions!");
     if (q.W > 32767) return fail(SS_ERR_DIMS, "image wider than 32767 columns does not fit int16 disparities");
+    if (q.H > 65535) return fail(SS_ERR_DIMS, "image taller than 65535 rows is not supported (one grid row per image row)");
+    if (q.maxD - q.minD > 65535) return fail(SS_ERR_PARAM, "more than 65536 disparity candidates are not supported");
     if (!(q.win > 0 && q.win % 2 == 1)) return fail(SS_ERR_WINSIZE, "winSize must be a positive odd number!");
     if (q.win > 255) return fail(SS_ERR_PARAM, "winSize > 255 is not supported");
     if (q.minD < 0) return fail(SS_ERR_PARAM, "minDisparity must be >= 0 (negative values read out of the row upstream)");
