@@ -49,15 +49,6 @@ namespace {
 
 typedef unsigned long long u64;
 
-#ifndef SS_PADROWS
-#define SS_PADROWS 1
-#endif
-#ifndef SS_SHEAR
-#define SS_SHEAR 1
-#endif
-#ifndef SS_SCALAR_ODD
-#define SS_SCALAR_ODD 1
-#endif
 #ifndef SS_UNROLL
 #define SS_UNROLL 2            // periods (8 window columns) per trip of the consumer loop: 1, 2 or 4
 #endif
@@ -666,9 +657,7 @@ struct WsSmem {         // stage s of a double-buffered region lives at base + s
     int e, f1, f2, pa, c1, c2, w1, w2, bars, total;
     int ebytes, f1bytes, f2bytes, pabytes, w1bytes, w2bytes;
 };
-__host__ __device__ inline WsSmem ws_smem(int win, int DC, int mode, bool gsw) {
-    const bool dual = mode == 1;
-    const int wstages = mode == 2 ? 3 : 2;
+__host__ __device__ inline WsSmem ws_smem(int win, int DC, bool gsw) {
     const int T = gsw ? TILE_X : TILE_WS, NU = T + win - 1, NR = T + DC - 1, NRp = T + DC, NV = NR + win - 1;
     const int EP = gsw ? DC * 4 : DC + 4;
     const int winq = (win + 3) >> 2;
@@ -678,17 +667,19 @@ __host__ __device__ inline WsSmem ws_smem(int win, int DC, int mode, bool gsw) {
     p.f1bytes = NU * 16;
     p.f2bytes = NV * 16;
     p.pabytes = winq * 16;
-    const int winr = SS_PADROWS ? (win + 3) & ~3 : win;          // weight rows per buffer
+    // weight buffers hold (win + 3) & ~3 rows: the producers store batches of 4 window offsets without predicates
+    // (rows past the window receive finite junk and are never read)
+    const int winr = (win + 3) & ~3;
     p.w1bytes = (winr * T * 4 + 15) & ~15;
-    p.w2bytes = ((winr * NRp * 4 + 15) & ~15) * (dual ? 2 : 1);  // dual: [V | V shifted by one column]
+    p.w2bytes = (winr * NRp * 4 + 15) & ~15;
     p.e = off;  off += 2 * p.ebytes;
     p.f1 = off; off += 2 * p.f1bytes;
     p.f2 = off; off += 2 * p.f2bytes;
     p.pa = off; off += 2 * p.pabytes;
     p.c1 = off; off += T * 16;
     p.c2 = off; off += NRp * 16;
-    p.w1 = off; off += wstages * p.w1bytes;
-    p.w2 = off; off += wstages * p.w2bytes;
+    p.w1 = off; off += 2 * p.w1bytes;
+    p.w2 = off; off += 2 * p.w2bytes;
     p.bars = off; off += 16 * 8;
     p.total = off;
     return p;
@@ -704,15 +695,12 @@ __device__ __forceinline__ float u8_to_f32(uint32_t w, int byte) {
     return f;
 }
 
-// DUAL: the right-weight rows are stored twice, the second copy shifted by one column, so that BOTH parities of
-// the (v[k], v[k+1]) pairs the packed multiply needs are 8-byte aligned register pairs straight out of LDS.128
-// (otherwise every odd-k pair costs two register moves per step: 20 of 80 consumer instructions).
-// MODE 0: one copy, 2 weight stages (large windows) | 1: dual copy, 2 stages | 2: one copy, 3 stages (absorbs
-// the skew between consumer warps: producers may run two window rows ahead)
-template <bool GSW, int DC, int REM, int MODE>
+// Variants measured and dropped: a second, one-column-shifted copy of the right-weight rows (aligned
+// odd pairs straight out of LDS.128, but 2x producer stores and 3 more loads per step), three weight stages, four
+// periods per loop trip, PRMT+FADD byte conversion.
+template <bool GSW, int DC, int REM>
 __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_aggregate_ws(const AggParams P) {
-    constexpr bool DUAL = MODE == 1;
-    constexpr int NWS = MODE == 2 ? 3 : 2;
+    constexpr int NWS = 2;                                   // weight stages
     typedef WsCfg<GSW, DC> C;
     constexpr int T = C::T, NRp = C::NRp, EP = C::EP, CW = C::CW, PW = C::PW;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -720,11 +708,10 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
     const Geom &g = P.g;
     const int win = g.win, pad = g.pad;
     const int NU = g.NU, NR = g.NR, NV = g.NV;
-    const WsSmem sp = ws_smem(win, DC, MODE, GSW);
+    const WsSmem sp = ws_smem(win, DC, GSW);
     const int winq = (win + 3) >> 2, winp = winq * 4;
-    const int w2copy = ((SS_PADROWS ? (win + 3) & ~3 : win) * NRp * 4 + 15) & ~15;   // bytes of one right-weight copy
     const uint32_t bar0 = smem_u32(smem + sp.bars);
-    // barrier slots: 0 centres | 1,2 fullF | 3,4 emptyF | 5-7 fullW | 8-10 emptyW | 11,12 fullE | 13,14 emptyE
+    // barrier slots: 0 centres | 1,2 fullF | 3,4 emptyF | 5,6 fullW | 8,9 emptyW | 11,12 fullE | 13,14 emptyE
     auto BAR = [&](int slot) { return bar0 + 8u * (uint32_t)slot; };
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -854,20 +841,11 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
                 // batches of 4 window offsets, two batches in flight: all loads first, stores last, so eight
                 // exp/sqrt chains overlap.  Offsets past the window (last batch) read finite padding of the staging
                 // buffers and are not stored.
-                // SS_PADROWS: the weight buffers hold (win + 3) & ~3 rows, so a batch of 4 is stored without
-                // predicates (rows past the window are written with finite junk and never read)
-                auto store4 = [&](float *d, int j0, float w0, float w1, float w2, float w3) {
+                auto store4 = [&](float *d, float w0, float w1, float w2, float w3) {
                     d[0] = w0;
-                    if (SS_PADROWS || j0 + 1 < win) d[pitch] = w1;
-                    if (SS_PADROWS || j0 + 2 < win) d[2 * pitch] = w2;
-                    if (SS_PADROWS || j0 + 3 < win) d[3 * pitch] = w3;
-                    if (DUAL && right && col > 0) {          // shifted copy: B[j][r-1] = V[j][r]
-                        float *dB = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(d) + w2copy) - 1;
-                        dB[0] = w0;
-                        if (SS_PADROWS || j0 + 1 < win) dB[pitch] = w1;
-                        if (SS_PADROWS || j0 + 2 < win) dB[2 * pitch] = w2;
-                        if (SS_PADROWS || j0 + 3 < win) dB[3 * pitch] = w3;
-                    }
+                    d[pitch] = w1;
+                    d[2 * pitch] = w2;
+                    d[3 * pitch] = w3;
                 };
 #pragma unroll 1
                 for (; jb < jend;) {
@@ -897,7 +875,7 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
                         w2 = support_weight<false>(c, n2, P.kC, t.z);
                         w3 = support_weight<false>(c, n3, P.kC, t.w);
                     }
-                    store4(dst, jb * 4, w0, w1, w2, w3);
+                    store4(dst, w0, w1, w2, w3);
                     nb += 4;
                     pa += 4;
                     dst += 4 * pitch;
@@ -925,11 +903,7 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
     // instead of four overlapping ones (shared-memory wavefronts, not issue slots, were the co-limiter: ncu 79 %).
     const int xl = lane >> 3, dl = lane & 7;
     const int xg = (warp / C::NDB) * 4 + xl;
-#if SS_SHEAR
     const int dg = ((warp % C::NDB) * 8 + dl + 2 * xl) % (DC / 4);
-#else
-    const int dg = (warp % C::NDB) * 8 + dl;
-#endif
     const int xb = 8 * xg;                                   // tile-relative first column
     const int kb = 4 * dg;                                   // chunk-relative first disparity
     // A warp none of whose lane tiles holds an evaluated pair (x - d < 0 everywhere, at the left image border, or d
@@ -981,45 +955,32 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
                 const float4 v1 = *reinterpret_cast<const float4 *>(w2p + s * NRp + 4);
                 const float4 v2 = *reinterpret_cast<const float4 *>(w2p + s * NRp + 8);
                 const float w1[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-                // right-weight pairs (v[k], v[k+1]): even k are the register pairs the loads produced; odd k either
-                // come from the shifted copy (DUAL) or straddle two loads and cost two moves each
+                // right-weight pairs (v[k], v[k+1]): even k are the register pairs the loads produced; odd k straddle two
+                // loads (two register moves before a packed op could read them) and are multiplied with scalar ops instead
                 const u64 VA[6] = {pk(v0.x, v0.y), pk(v0.z, v0.w), pk(v1.x, v1.y), pk(v1.z, v1.w), pk(v2.x, v2.y), pk(v2.z, v2.w)};
                 const float vf[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-                u64 VM[5];
-                if (DUAL) {
-                    const float *w2b = reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(w2p) + w2copy);
-                    const float4 u0 = *reinterpret_cast<const float4 *>(w2b + s * NRp);
-                    const float4 u1 = *reinterpret_cast<const float4 *>(w2b + s * NRp + 4);
-                    const float2 u2 = *reinterpret_cast<const float2 *>(w2b + s * NRp + 8);
-                    VM[0] = pk(u0.x, u0.y); VM[1] = pk(u0.z, u0.w); VM[2] = pk(u1.x, u1.y); VM[3] = pk(u1.z, u1.w); VM[4] = pk(u2.x, u2.y);
-                } else {
-                    VM[0] = pk(v0.y, v0.z); VM[1] = pk(v0.w, v1.x); VM[2] = pk(v1.y, v1.z); VM[3] = pk(v1.w, v2.x); VM[4] = pk(v2.y, v2.z);
-                }
 #pragma unroll
                 for (int a = 0; a < 8; ++a) {
                     const u64 w1d = pk(w1[a], w1[a]);
 #pragma unroll
                     for (int bp = 0; bp < 2; ++bp) {
                         const int k = 7 - a + 2 * bp;                   // reversed right index of disparity kb+2bp
-                        const u64 w2d = (k & 1) ? VM[k >> 1] : VA[k >> 1];
                         const u64 e2 = ring[(a + s) & 7][bp];
-                        // SS_SCALAR_ODD: an odd-k pair (v[k], v[k+1]) straddles two loaded register pairs and costs two
-                        // moves before a packed op can read it.  Two scalar ops (1 issue cycle each, same rounding) write
-                        // the halves of an aligned pair directly: 2 cycles instead of 2 (packed) + 2 (moves).
+                        // Odd k: two scalar ops (1 issue cycle each, same rounding as the packed form) write the halves
+                        // of an aligned pair directly: 2 cycles instead of 2 (packed) + 2 (pair-building moves).
                         if (GSW) {
                             acc0[a][bp] = fma2(w1d, e2, acc0[a][bp]);   // left-reference cost  (_passive.cpp:528)
-                            if (SS_SCALAR_ODD && !DUAL && (k & 1)) {    // right-reference cost (:644)
+                            if (k & 1) {                                // right-reference cost (:644)
                                 float elo, ehi, alo, ahi;
                                 upk(e2, elo, ehi);
                                 upk(acc1[a][bp], alo, ahi);
                                 acc1[a][bp] = pk(__fmaf_rn(vf[k], elo, alo), __fmaf_rn(vf[k + 1], ehi, ahi));
                             } else {
-                                acc1[a][bp] = fma2(w2d, e2, acc1[a][bp]);
+                                acc1[a][bp] = fma2(VA[k >> 1], e2, acc1[a][bp]);
                             }
                         } else {
-                            const u64 ww = (SS_SCALAR_ODD && !DUAL && (k & 1))
-                                               ? pk(__fmul_rn(w1[a], vf[k]), __fmul_rn(w1[a], vf[k + 1]))
-                                               : mul2(w1d, w2d);        // w1*w2
+                            const u64 ww = (k & 1) ? pk(__fmul_rn(w1[a], vf[k]), __fmul_rn(w1[a], vf[k + 1]))
+                                                   : mul2(w1d, VA[k >> 1]);     // w1*w2
                             acc0[a][bp] = fma2(ww, e2, acc0[a][bp]);    // cost += w1*w2*e  (_passive.cpp:77)
                             acc1[a][bp] = add2(acc1[a][bp], ww);        // tot  += w1*w2    (:82)
                         }
@@ -1263,7 +1224,7 @@ struct Ctx {
     double agg_ms_done = 0;
     long long agg_launches = 0, total_launches = 0;
     int smem_attr_val[2][12] = {};   // largest dynamic-smem opt-in set so far, per k_aggregate instantiation
-    int smem_attr_ws[72] = {};       // same for k_aggregate_ws
+    int smem_attr_ws[24] = {};       // same for k_aggregate_ws
 };
 
 Ctx g_ctx;
@@ -1425,14 +1386,14 @@ int launch_aggregate_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
     return SS_OK;
 }
 
-template <bool GSW, int DC, int REM, int MODE>
+template <bool GSW, int DC, int REM>
 int launch_ws_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
     typedef WsCfg<GSW, DC> C;
-    const WsSmem sp = ws_smem(P.g.win, DC, MODE, GSW);
+    const WsSmem sp = ws_smem(P.g.win, DC, GSW);
     if (sp.total > 227 * 1024) return fail(SS_ERR_PARAM, "winSize too large for the shared-memory tiling of k_aggregate_ws");
-    const int di = (((DC == 128 ? 2 : (DC == 64 ? 1 : 0)) * 4 + REM / 2) * 3 + MODE) * 2 + (GSW ? 1 : 0);
+    const int di = ((DC == 128 ? 2 : (DC == 64 ? 1 : 0)) * 4 + REM / 2) * 2 + (GSW ? 1 : 0);
     if (c.smem_attr_ws[di] < sp.total) {
-        CU_TRY(cudaFuncSetAttribute(k_aggregate_ws<GSW, DC, REM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+        CU_TRY(cudaFuncSetAttribute(k_aggregate_ws<GSW, DC, REM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
         c.smem_attr_ws[di] = sp.total;
     }
     dim3 grid(P.g.ntx, P.g.row1 - P.g.row0, P.g.nch);
@@ -1442,7 +1403,7 @@ int launch_ws_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
         CU_TRY(cudaEventCreate(&e1));
         CU_TRY(cudaEventRecord(e0, st));
     }
-    k_aggregate_ws<GSW, DC, REM, MODE><<<grid, C::NT, sp.total, st>>>(P);
+    k_aggregate_ws<GSW, DC, REM><<<grid, C::NT, sp.total, st>>>(P);
     CU_TRY(cudaGetLastError());
     if (c.profile) {
         CU_TRY(cudaEventRecord(e1, st));
@@ -1453,30 +1414,17 @@ int launch_ws_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
     return SS_OK;
 }
 
-template <bool GSW, int DC, int MODE>
-int launch_ws_mode(Ctx &c, const AggParams &P, cudaStream_t st) {
-    switch (P.g.win & 7) {          // win is odd
-        case 1: return launch_ws_rem<GSW, DC, 1, MODE>(c, P, st);
-        case 3: return launch_ws_rem<GSW, DC, 3, MODE>(c, P, st);
-        case 5: return launch_ws_rem<GSW, DC, 5, MODE>(c, P, st);
-        default: return launch_ws_rem<GSW, DC, 7, MODE>(c, P, st);
-    }
-}
-
-// true when the warp-specialised kernel can stage this window in shared memory at all
-bool ws_fits(int win, int DC, bool gsw) { return ws_smem(win, DC, 0, gsw).total <= 227 * 1024; }
+// true when the warp-specialised kernel can stage this window in shared memory
+bool ws_fits(int win, int DC, bool gsw) { return ws_smem(win, DC, gsw).total <= 227 * 1024; }
 
 template <bool GSW, int DC>
 int launch_ws(Ctx &c, const AggParams &P, cudaStream_t st) {
-    // weight-buffer organisation, best first, limited by the per-SM share of shared memory
-    const int budget = 227 * 1024 / WsCfg<GSW, DC>::MINB - 1024;
-    int mode = getenv("SS_WS_MODE") ? atoi(getenv("SS_WS_MODE")) : -1;
-    // default: single right-weight copy (mode 0).  The dual copy trades 10 register moves per step for three more
-    // shared-memory loads and doubles the producers' stores; measured 4 % slower at C2 (9.95 vs 9.58 ms).
-    if (mode < 0 || mode > 2 || ws_smem(P.g.win, DC, mode, GSW).total > budget) mode = 0;
-    if (mode == 2) return launch_ws_mode<GSW, DC, 2>(c, P, st);
-    if (mode == 1) return launch_ws_mode<GSW, DC, 1>(c, P, st);
-    return launch_ws_mode<GSW, DC, 0>(c, P, st);
+    switch (P.g.win & 7) {          // win is odd
+        case 1: return launch_ws_rem<GSW, DC, 1>(c, P, st);
+        case 3: return launch_ws_rem<GSW, DC, 3>(c, P, st);
+        case 5: return launch_ws_rem<GSW, DC, 5>(c, P, st);
+        default: return launch_ws_rem<GSW, DC, 7>(c, P, st);
+    }
 }
 
 template <bool GSW, int DC>
