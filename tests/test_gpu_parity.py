@@ -353,3 +353,31 @@ def test_gsw_large_window_falls_back_to_single_role_kernel(monkeypatch):
     assert np.allclose(ws["cost_left"][fin], single["cost_left"][fin], rtol=2e-5, atol=1e-5)
     assert np.allclose(ws["cost_right"][fin], single["cost_right"][fin], rtol=2e-5, atol=1e-5)
     assert (ws["final"] != single["final"]).mean() < 0.01
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: a plain-C program (tests/c_abi_smoke.c, compiled here with gcc against
+    include/*.h and libsspassive.so) must produce the same bytes as the Python mirror."""
+    import shutil
+    import subprocess
+    from simplestereo_b200 import _cabi
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = tmp_path / "c_abi_smoke"
+    libdir = os.path.dirname(_cabi.LIB_PATH)
+    subprocess.run(["gcc", "-O1", "-o", str(exe), os.path.join(here, "c_abi_smoke.c"), "-L" + libdir, "-lsspassive",
+                    "-Wl,-rpath," + libdir], check=True)
+    l, r, _ = synth_pair(150, 40, 24, 21)
+    l.tofile(tmp_path / "l.bgr")
+    r.tofile(tmp_path / "r.bgr")
+    out = subprocess.run([str(exe), str(tmp_path / "l.bgr"), str(tmp_path / "r.bgr"), "150", "40", str(tmp_path / "o")],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    asw = np.fromfile(tmp_path / "o.asw.i16", np.int16).reshape(40, 150)
+    gsw = np.fromfile(tmp_path / "o.gsw.i16", np.int16).reshape(40, 150)
+    pts = np.fromfile(tmp_path / "o.pts.f32", np.float32).reshape(40, 150, 3)
+    assert np.array_equal(asw, ss.passive.StereoASW(9, 24, 0, 5.0, 17.5, True).compute(l, r))
+    assert np.array_equal(gsw, ss.passive.StereoGSW(7, 24, 0, 10, 120.0, 3, 20).compute(l, r))
+    d = ss.passive.StereoASW(9, 24, 0, 5.0, 17.5, False).compute(l, r)
+    assert np.array_equal(pts, ss.points.getAdimensional3DPoints(d), equal_nan=True)
