@@ -18,6 +18,8 @@ A "step" is one full disparity map of that pair.
           SURVEY.md 8d), with achieved HBM GB/s against MEASURED_PEAKS.json beside it.
   cpu_baseline  the unmodified reference (oracle/_ref) timed on this box's host cores on a bounded full-width
           crop and extrapolated by exact window-element counts (N=1, rank 0 only).
+  other_configs  device-resident ms of the other BASELINE.json configurations (C2 + L-R, C3 GSW, C4, C5) on one GPU,
+          for context only (N=1; --no-other-configs skips them).
 
 At N > 1 the frame is sharded into N image-row stripes (one rank per GPU) and reassembled with one NCCL
 all-gather (strong scaling: total work fixed).
@@ -386,6 +388,42 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": bytes_per_launch},
     }
 
+    # the other BASELINE.json configurations, device-resident, for context (parity for them lives in tests/)
+    others = None
+    if world == 1 and not args.no_other_configs:
+        others = {}
+        specs = {"C2+LR 1242x375 D128 win35 consistent": (1242, 375, 35, 127, "asw", 1),
+                 "C3 GSW 1242x375 D128 win35": (1242, 375, 35, 127, "gsw", 1),
+                 "C4 2880x1988 D256 win51 consistent": (2880, 1988, 51, 255, "asw", 1),
+                 "C5 3840x2160 D512 win35 (one GPU)": (3840, 2160, 35, 511, "asw", 0)}
+        for name, (w, h, win, maxd, kind, cons) in specs.items():
+            try:
+                l2, r2, _ = synth_pair(w, h, maxd, 0)
+                a, b = torch.from_numpy(l2).to(dev), torch.from_numpy(r2).to(dev)
+                o = torch.empty((h, w), dtype=torch.int16, device=dev)
+
+                def run():
+                    if kind == "asw":
+                        _cabi.check(L.ss_asw_compute_device(a.data_ptr(), b.data_ptr(), w, h, win, maxd, 0, GC, GP, cons, 0, h,
+                                                            o.data_ptr(), stream.cuda_stream))
+                    else:
+                        _cabi.check(L.ss_gsw_compute_device(a.data_ptr(), b.data_ptr(), w, h, win, maxd, 0, 10, 120.0, 3, 20, 0, h,
+                                                            o.data_ptr(), stream.cuda_stream))
+                run()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                run()
+                run()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 2
+                others[name] = {"ms": round(ms, 3), "Mpix_disp_per_s": round(w * h * (maxd + 1) / ms / 1e3, 1)}
+                del a, b, o
+            except Exception as ex:
+                others[name] = {"error": repr(ex)[:120]}
+        torch.cuda.empty_cache()
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -407,6 +445,7 @@ def run_b200(args):
         "gpu_launches": int(total_launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "other_configs": others,
         "wall_s_timed_region": t_wall,
     }
     print(json.dumps(line), flush=True)
@@ -422,6 +461,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -34,7 +34,7 @@ for r in rows:
     n = r[ik][:48]
     a = tot.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += v
 s = sum(v for _, v in tot.values())
-out = ["ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 2 --warmup 1 --no-cpu-baseline", "",
+out = ["ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-other-configs", "",
        "kernel | launches | total ms | share", "---|---|---|---"]
 for n, (c, v) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     out.append(f"{n} | {c} | {v:.3f} | {100 * v / s:.1f}%")
