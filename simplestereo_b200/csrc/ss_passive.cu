@@ -1059,6 +1059,8 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
     }
 }
 
+#include "ss_aggregate_tc.cuh"
+
 // ------------------------------------------------------------------------------------------
 // k_wta_right: right-reference winners = minimum over diagonals of the aggregated volume
 // (_passive.cpp:209-248; d ascending, strict '<' => smallest disparity wins)
@@ -1225,6 +1227,7 @@ struct Ctx {
     long long agg_launches = 0, total_launches = 0;
     int smem_attr_val[2][12] = {};   // largest dynamic-smem opt-in set so far, per k_aggregate instantiation
     int smem_attr_ws[24] = {};       // same for k_aggregate_ws
+    int smem_attr_tc[4] = {};        // same for k_aggregate_tc
 };
 
 Ctx g_ctx;
@@ -1292,6 +1295,7 @@ int ctx_init(int device) {
         c.prox_win = -1;
         memset(c.smem_attr_val, 0, sizeof(c.smem_attr_val));
         memset(c.smem_attr_ws, 0, sizeof(c.smem_attr_ws));
+        memset(c.smem_attr_tc, 0, sizeof(c.smem_attr_tc));
     }
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
@@ -1412,6 +1416,45 @@ int launch_ws_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
     c.agg_launches++;
     c.total_launches++;
     return SS_OK;
+}
+
+// ASW, 128-disparity chunks, win <= 39: denominators on the tensor cores (ss_aggregate_tc.cuh)
+template <int REM>
+int launch_tc_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
+    const TcSmem sp = tc_smem(P.g.win);
+    if (c.smem_attr_tc[REM / 2] < sp.total) {
+        CU_TRY(cudaFuncSetAttribute(k_aggregate_tc<REM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+        c.smem_attr_tc[REM / 2] = sp.total;
+    }
+    dim3 grid(P.g.ntx, P.g.row1 - P.g.row0, P.g.nch);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c.profile) {
+        CU_TRY(cudaEventCreate(&e0));
+        CU_TRY(cudaEventCreate(&e1));
+        CU_TRY(cudaEventRecord(e0, st));
+    }
+    k_aggregate_tc<REM><<<grid, 512, sp.total, st>>>(P);
+    CU_TRY(cudaGetLastError());
+    if (c.profile) {
+        CU_TRY(cudaEventRecord(e1, st));
+        c.events.emplace_back(e0, e1);
+    }
+    c.agg_launches++;
+    c.total_launches++;
+    return SS_OK;
+}
+int launch_tc(Ctx &c, const AggParams &P, cudaStream_t st) {
+    switch (P.g.win & 7) {
+        case 1: return launch_tc_rem<1>(c, P, st);
+        case 3: return launch_tc_rem<3>(c, P, st);
+        case 5: return launch_tc_rem<5>(c, P, st);
+        default: return launch_tc_rem<7>(c, P, st);
+    }
+}
+bool tc_usable(const Geom &g) {
+    if (g.DC != 128 || g.win > 39 || tc_smem(g.win).total > 227 * 1024) return false;
+    const char *e = getenv("SS_TCDEN");
+    return !(e && atoi(e) == 0);
 }
 
 // true when the warp-specialised kernel can stage this window in shared memory
@@ -1550,6 +1593,8 @@ int run_device(Ctx &c, const Call &q, const uint8_t *d_img1, const uint8_t *d_im
             if (g.DC == 128) rc = launch_ws<true, 128>(c, P, st);
             else if (g.DC == 64) rc = launch_ws<true, 64>(c, P, st);
             else rc = launch_ws<true, 32>(c, P, st);
+        } else if (tc_usable(g)) {
+            rc = launch_tc(c, P, st);
         } else {
             if (g.DC == 128) rc = launch_ws<false, 128>(c, P, st);
             else if (g.DC == 64) rc = launch_ws<false, 64>(c, P, st);
@@ -1691,6 +1736,7 @@ int ss_shutdown(void) {
     c.ready = false;
     memset(c.smem_attr_val, 0, sizeof(c.smem_attr_val));
     memset(c.smem_attr_ws, 0, sizeof(c.smem_attr_ws));
+    memset(c.smem_attr_tc, 0, sizeof(c.smem_attr_tc));
     return SS_OK;
 }
 
