@@ -380,7 +380,7 @@ def run_b200(args):
     roofline = {
         "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
         "traffic": traffic,
-        "kernel": "k_aggregate_ws<ASW, DC=128> (warp-specialised support-weight aggregation + WTA)", "kernel_ms": agg_avg_s * 1e3, "kernel_share_of_step": agg_ms / total_ms if world == 1 else None,
+        "kernel": "k_aggregate_tc<ASW, DC=128> (warp-specialised support-weight aggregation + WTA; numerators on packed FP32, denominators on tcgen05 3xTF32)", "kernel_ms": agg_avg_s * 1e3, "kernel_share_of_step": agg_ms / total_ms if world == 1 else None,
         "peak_source": "FFMA-only microbenchmark run live on this GPU (ss_measure_fp32_peak); nominal 74.4 TFLOP/s",
         "algorithmic_flops_per_launch": flops_per_launch,
         "hbm": {"achieved": bytes_per_launch / agg_avg_s / 1e9, "peak": hbm_peak, "unit": "GB/s",

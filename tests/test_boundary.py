@@ -41,6 +41,8 @@ def test_library_is_sm100a_and_uses_tma_and_packed_fp32():
     sass = subprocess.run(["cuobjdump", "-sass", _cabi.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass          # cp.async.bulk (TMA) staging of window rows
     assert "FFMA2" in sass           # packed fp32 accumulation
+    assert "UTCHMMA" in sass         # tcgen05.mma: the ASW denominators (k_aggregate_tc)
+    assert "STTM" in sass and "LDTM" in sass   # tcgen05.st / tcgen05.ld: right weights into, denominators out of TMEM
 
 
 def test_python_side_validation_without_gpu():

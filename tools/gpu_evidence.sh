@@ -12,7 +12,7 @@ python tools/time_configs.py c1 c2 c2c c3 c4 c5 > $O/configs.txt 2>&1; cat $O/co
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-other-configs > $O/launches_bench.log 2>&1
 # the dominant kernels, full set, one launch each
-ncu --set full --clock-control none --import-source on -k regex:k_aggregate_ws -s 1 -c 1 -o $O/asw_ws \
+ncu --set full --clock-control none --import-source on -k regex:k_aggregate_tc -s 1 -c 1 -o $O/asw_ws \
     python tools/time_configs.py c2 reps=1 > $O/ncu_asw.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_aggregate_ws -s 1 -c 1 -o $O/gsw_ws \
     python tools/time_configs.py c3 reps=1 > $O/ncu_gsw.log 2>&1
