@@ -1,5 +1,5 @@
 // ss_aggregate_tc.cuh -- k_aggregate_tc: the ASW aggregation kernel with the DENOMINATORS on the tensor cores.
-// Included by ss_passive.cu after k_aggregate_ws (shares its helpers).  ASW only, DC = 128, T = 96, win <= 39.
+// Included by ss_passive.cu after k_aggregate_ws (shares its helpers).  ASW only, DC = 128, T = 96, win <= 79.
 //
 // den[x][d] = sum_q w1[x][q] * w2[x-d][q] is a banded GEMM: per window row, D[r][x] += W2[r][j] * W1[x][j]
 // with r the reversed right-centre index (den[x][d] = D[T-1-x+d][x]).  The numerator carries a per-(x,d,q) factor and
@@ -16,7 +16,10 @@
 //     serves the consumers (one LDS.128 = one column's weights for 4 consecutive window offsets).
 //   * the accumulator (2 x 128 lanes x 96 columns) stays in TMEM for the whole block; after the last window row the
 //     producers read it back (tcgen05.ld) into shared memory in [r][x] order and the consumers pick their 32 values.
-//   * TMEM map (512 columns): D half h at 96 h; A at 192 + 160 stage + 80 half + 40 (hi|lo) + j.
+//   * TMEM map (512 columns): D half h at 96 h; A at 192 + 160 stage + 80 half + 40 (hi|lo) + j  (win <= 39).
+//     SINGLE (39 < win <= 79): one stage of A, 192 + 2 KC half + KC (hi|lo) + j with KC = 8 ceil(win / 8), and one stage of
+//     the left-weight residual in shared memory; the producers then wait for the previous row's MMAs (a second commit onto
+//     barrier 7) before they overwrite them -- a stall of one MMA batch per window row instead of a second buffer.
 //   * one thread (producer 3, lane 0) issues the 30 tcgen05.mma per window row and commits them onto the "weight stage
 //     free" mbarrier, whose count is consumers + 1.
 
@@ -27,9 +30,10 @@ constexpr int TC_DS_BYTES = 224 * TILE_WS * 4;    // denominators read back: [r]
 
 struct TcSmem {
     int e, f1, f2, pa, c1, c2, w1, w2, ds, total;
-    int ebytes, f1bytes, f2bytes, pabytes, w1arr, w1bytes, w2bytes;
+    int ebytes, f1bytes, f2bytes, pabytes, w1arr, w2bytes;
 };
-__host__ __device__ inline TcSmem tc_smem(int win) {
+// left-weight operand region: [hi stage 0 | hi stage 1 | lo stage 0 | lo stage 1 (absent when single)]
+__host__ __device__ inline TcSmem tc_smem(int win, bool single) {
     const int T = TILE_WS, DC = 128, NU = T + win - 1, NR = T + DC - 1, NRp = T + DC, NV = NR + win - 1, EP = DC + 4;
     const int winq = (win + 3) >> 2, winr = winq * 4, KG = (win + 7) >> 3;
     TcSmem p;
@@ -38,7 +42,6 @@ __host__ __device__ inline TcSmem tc_smem(int win) {
     p.f2bytes = NV * 16;
     p.pabytes = winq * 16;
     p.w1arr = KG * TC_KGB;
-    p.w1bytes = 2 * p.w1arr;                       // [hi | lo]
     p.w2bytes = (winr * NRp * 4 + 15) & ~15;
     int off = 256;                                 // header: 16 mbarriers + the TMEM base address
     p.ds = off;
@@ -48,7 +51,7 @@ __host__ __device__ inline TcSmem tc_smem(int win) {
     p.pa = off; off += 2 * p.pabytes;
     p.c1 = off; off += T * 16;
     p.c2 = off; off += NRp * 16;
-    p.w1 = off; off += 2 * p.w1bytes;
+    p.w1 = off; off += (single ? 3 : 4) * p.w1arr;
     p.w2 = off; off += 2 * p.w2bytes;
     p.total = off > p.ds + TC_DS_BYTES ? off : p.ds + TC_DS_BYTES;
     return p;
@@ -67,7 +70,7 @@ __device__ __forceinline__ void tc_st4(uint32_t taddr, uint32_t a, uint32_t b, u
 }
 __device__ __forceinline__ float tc_lo(float w) { return __fsub_rn(w, __uint_as_float(__float_as_uint(w) & 0xffffe000u)); }
 
-template <int REM>
+template <int REM, bool SINGLE>
 __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
     constexpr int DC = 128, T = TILE_WS, NRp = T + DC, EP = DC + 4, CW = 12, PW = 4, NDB = 4, NT = 512;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -75,11 +78,12 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
     const Geom &g = P.g;
     const int win = g.win, pad = g.pad;
     const int NU = g.NU, NR = g.NR, NV = g.NV;
-    const TcSmem sp = tc_smem(win);
+    const TcSmem sp = tc_smem(win, SINGLE);
     const int winq = (win + 3) >> 2, winp = winq * 4, KG = (win + 7) >> 3;
+    const uint32_t KC = SINGLE ? 8u * (uint32_t)KG : 40u;     // TMEM columns per (half, hi|lo) block of A
     const uint32_t bar0 = smem_u32(smem);
     // barrier slots: 0 centres | 1,2 fullF | 3,4 emptyF | 5,6 fullW | 8,9 emptyW (consumers + MMA commit) | 11,12 fullE |
-    //                13,14 emptyE | 15 denominators read back
+    //                13,14 emptyE | 15 denominators read back | 7 (SINGLE) MMAs of the previous window row done
     auto BAR = [&](int slot) { return bar0 + 8u * (uint32_t)slot; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 128);
 
@@ -120,13 +124,17 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
             mbar_init(BAR(13 + s), CW);
         }
         mbar_init(BAR(15), PW);
+        mbar_init(BAR(7), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tbase = *tmem_slot;
-    auto colA = [&](int stage, int half, int lo) { return 192u + (uint32_t)stage * 160u + (uint32_t)half * 80u + (uint32_t)lo * 40u; };
+    auto colA = [&](int stage, int half, int lo) {
+        return SINGLE ? 192u + (uint32_t)half * 2u * KC + (uint32_t)lo * KC
+                      : 192u + (uint32_t)stage * 160u + (uint32_t)half * 80u + (uint32_t)lo * 40u;
+    };
 
     if (warp >= CW) {
         // =================================== producers ===================================
@@ -163,8 +171,8 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
         }
         // K padding: window offsets in [win, 8 KG) must contribute 0.  Zero every A column of this warp's TMEM lanes and
         // the whole left-weight operand once; offsets inside the last written batch are zeroed when they are written.
-        for (int c = 0; c < 320; c += 4) tc_st4(tbase + lane_base + 192u + c, 0u, 0u, 0u, 0u);
-        for (int k = (pw * 32 + lane) * 16; k < 2 * sp.w1bytes; k += PW * 32 * 16)
+        for (int c = 0; c < (SINGLE ? (int)(4u * KC) : 320); c += 4) tc_st4(tbase + lane_base + 192u + c, 0u, 0u, 0u, 0u);
+        for (int k = (pw * 32 + lane) * 16; k < (SINGLE ? 3 : 4) * sp.w1arr; k += PW * 32 * 16)
             *reinterpret_cast<float4 *>(smem + sp.w1 + k) = make_float4(0.f, 0.f, 0.f, 0.f);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");              // the producers' own barrier: zeroing done everywhere
@@ -175,7 +183,7 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
         const int l0 = pw == 0 ? 0 : pw == 1 ? (NB * 5) / 9 : pw == 2 ? (NB * 11) / 9 : (NB * 16) / 9;
         const int l1 = pw == 0 ? (NB * 5) / 9 : pw == 1 ? (NB * 11) / 9 : pw == 2 ? (NB * 16) / 9 : 3 * NB;
         const int o_f1 = sp.f1, o_f2 = sp.f2, o_pa = sp.pa, o_w1 = sp.w1, o_w2 = sp.w2;
-        const int b_f1 = sp.f1bytes, b_f2 = sp.f2bytes, b_pa = sp.pabytes, b_w1 = sp.w1bytes, b_w2 = sp.w2bytes, w1arr = sp.w1arr;
+        const int b_f1 = sp.f1bytes, b_f2 = sp.f2bytes, b_pa = sp.pabytes, b_w2 = sp.w2bytes, w1arr = sp.w1arr;
 
         int sw = 0, phw = 0;
         for (int n = 0; n < nsteps; ++n) {
@@ -192,12 +200,14 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
             if (n == 0) mbar_wait(BAR(0), 0);
             mbar_wait(BAR(1 + st), ph);            // features of this window row have landed
             mbar_wait_long(BAR(8 + sw), phw ^ 1);  // consumers AND the tensor core are done with this weight stage
+            if (SINGLE && n > 0) mbar_wait(BAR(7), (n - 1) & 1);   // single-stage operands: the previous row's MMAs have read them
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
             const float4 *f1 = reinterpret_cast<const float4 *>(smem + o_f1 + st * b_f1);
             const float4 *f2 = reinterpret_cast<const float4 *>(smem + o_f2 + st * b_f2);
             const float *parg = reinterpret_cast<const float *>(smem + o_pa + st * b_pa);
-            unsigned char *W1hi = smem + o_w1 + sw * b_w1;
+            unsigned char *W1hi = smem + o_w1 + sw * w1arr;
+            unsigned char *W1lo = smem + o_w1 + (2 + (SINGLE ? 0 : sw)) * w1arr;
             float *W2s = reinterpret_cast<float *>(smem + o_w2 + sw * b_w2);
 
             // ---- right columns: consumer copy (row-major, reversed index) + tensor-memory copy (hi, lo) ----
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
                     }
                     dst[0] = w0; dst[NRp] = w1; dst[2 * NRp] = w2; dst[3 * NRp] = w3;
                     tc_st4(ta + 4 * jb, __float_as_uint(w0), __float_as_uint(w1), __float_as_uint(w2), __float_as_uint(w3));
-                    tc_st4(ta + 40 + 4 * jb, __float_as_uint(tc_lo(w0)), __float_as_uint(tc_lo(w1)), __float_as_uint(tc_lo(w2)),
+                    tc_st4(ta + KC + 4 * jb, __float_as_uint(tc_lo(w0)), __float_as_uint(tc_lo(w1)), __float_as_uint(tc_lo(w2)),
                            __float_as_uint(tc_lo(w3)));
                     nb += 4;
                     dst += 4 * NRp;
@@ -248,9 +258,9 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
                     if (4 * jb + 2 >= win) w2 = 0.f;
                     w3 = 0.f;
                 }
-                unsigned char *q = W1hi + (jb >> 1) * TC_KGB + (jb & 1) * TC_LBO + (col >> 3) * TC_SBO + (col & 7) * 16;
-                *reinterpret_cast<float4 *>(q) = make_float4(w0, w1, w2, w3);
-                *reinterpret_cast<float4 *>(q + w1arr) = make_float4(tc_lo(w0), tc_lo(w1), tc_lo(w2), tc_lo(w3));
+                const int qo = (jb >> 1) * TC_KGB + (jb & 1) * TC_LBO + (col >> 3) * TC_SBO + (col & 7) * 16;
+                *reinterpret_cast<float4 *>(W1hi + qo) = make_float4(w0, w1, w2, w3);
+                *reinterpret_cast<float4 *>(W1lo + qo) = make_float4(tc_lo(w0), tc_lo(w1), tc_lo(w2), tc_lo(w3));
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -266,7 +276,7 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
                     const uint32_t idesc = tc_idesc(128, T);
-                    const uint32_t bhi = smem_u32(W1hi), blo = bhi + (uint32_t)w1arr;
+                    const uint32_t bhi = smem_u32(W1hi), blo = smem_u32(W1lo);
                     for (int half = 0; half < 2; ++half)
                         for (int term = 0; term < 3; ++term) {
                             const uint32_t a0 = tbase + colA(sw, half, term == 2);
@@ -280,8 +290,11 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
                                              : "memory");
                             }
                         }
-                    // completion of everything issued so far arrives on "weight stage free"
+                    // completion of everything issued so far arrives on "weight stage free" (and on barrier 7 when the
+                    // operands are single-staged)
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(8 + sw)) : "memory");
+                    if (SINGLE)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(7)) : "memory");
                 }
                 __syncwarp();
             }
@@ -349,7 +362,7 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
             for (int a = 0; a < 7; ++a) load_e(ep + a * EP, ring[a][0], ring[a][1]);
             ep += 7 * EP;
             // left weights: K-major operand, one 16-byte chunk = one column x, 4 consecutive window offsets
-            const unsigned char *w1q = smem + (sp.w1 + sw * sp.w1bytes) + xg * TC_SBO;
+            const unsigned char *w1q = smem + (sp.w1 + sw * sp.w1arr) + xg * TC_SBO;
             const float *w2p = reinterpret_cast<const float *>(smem + (sp.w2 + sw * sp.w2bytes)) + R0;
             float4 wq[8];
 

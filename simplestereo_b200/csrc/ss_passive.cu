@@ -1227,7 +1227,7 @@ struct Ctx {
     long long agg_launches = 0, total_launches = 0;
     int smem_attr_val[2][12] = {};   // largest dynamic-smem opt-in set so far, per k_aggregate instantiation
     int smem_attr_ws[24] = {};       // same for k_aggregate_ws
-    int smem_attr_tc[4] = {};        // same for k_aggregate_tc
+    int smem_attr_tc[8] = {};        // same for k_aggregate_tc
 };
 
 Ctx g_ctx;
@@ -1418,13 +1418,15 @@ int launch_ws_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
     return SS_OK;
 }
 
-// ASW, 128-disparity chunks, win <= 39: denominators on the tensor cores (ss_aggregate_tc.cuh)
-template <int REM>
+// ASW, 128-disparity chunks: denominators on the tensor cores (ss_aggregate_tc.cuh).  win <= 39: two stages of operands in
+// tensor memory; 39 < win <= 79: one stage (SINGLE).
+template <int REM, bool SINGLE>
 int launch_tc_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
-    const TcSmem sp = tc_smem(P.g.win);
-    if (c.smem_attr_tc[REM / 2] < sp.total) {
-        CU_TRY(cudaFuncSetAttribute(k_aggregate_tc<REM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
-        c.smem_attr_tc[REM / 2] = sp.total;
+    const TcSmem sp = tc_smem(P.g.win, SINGLE);
+    int &attr = c.smem_attr_tc[(REM / 2) * 2 + (SINGLE ? 1 : 0)];
+    if (attr < sp.total) {
+        CU_TRY(cudaFuncSetAttribute(k_aggregate_tc<REM, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sp.total));
+        attr = sp.total;
     }
     dim3 grid(P.g.ntx, P.g.row1 - P.g.row0, P.g.nch);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1433,7 +1435,7 @@ int launch_tc_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
         CU_TRY(cudaEventCreate(&e1));
         CU_TRY(cudaEventRecord(e0, st));
     }
-    k_aggregate_tc<REM><<<grid, 512, sp.total, st>>>(P);
+    k_aggregate_tc<REM, SINGLE><<<grid, 512, sp.total, st>>>(P);
     CU_TRY(cudaGetLastError());
     if (c.profile) {
         CU_TRY(cudaEventRecord(e1, st));
@@ -1443,16 +1445,20 @@ int launch_tc_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
     c.total_launches++;
     return SS_OK;
 }
-int launch_tc(Ctx &c, const AggParams &P, cudaStream_t st) {
+template <bool SINGLE>
+int launch_tc_s(Ctx &c, const AggParams &P, cudaStream_t st) {
     switch (P.g.win & 7) {
-        case 1: return launch_tc_rem<1>(c, P, st);
-        case 3: return launch_tc_rem<3>(c, P, st);
-        case 5: return launch_tc_rem<5>(c, P, st);
-        default: return launch_tc_rem<7>(c, P, st);
+        case 1: return launch_tc_rem<1, SINGLE>(c, P, st);
+        case 3: return launch_tc_rem<3, SINGLE>(c, P, st);
+        case 5: return launch_tc_rem<5, SINGLE>(c, P, st);
+        default: return launch_tc_rem<7, SINGLE>(c, P, st);
     }
 }
+int launch_tc(Ctx &c, const AggParams &P, cudaStream_t st) {
+    return P.g.win <= 39 ? launch_tc_s<false>(c, P, st) : launch_tc_s<true>(c, P, st);
+}
 bool tc_usable(const Geom &g) {
-    if (g.DC != 128 || g.win > 39 || tc_smem(g.win).total > 227 * 1024) return false;
+    if (g.DC != 128 || g.win > 79 || tc_smem(g.win, g.win > 39).total > 227 * 1024) return false;
     const char *e = getenv("SS_TCDEN");
     return !(e && atoi(e) == 0);
 }
