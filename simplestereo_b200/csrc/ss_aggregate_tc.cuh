@@ -16,6 +16,13 @@
 //     serves the consumers (one LDS.128 = one column's weights for 4 consecutive window offsets).
 //   * the accumulator (2 x 128 lanes x 96 columns) stays in TMEM for the whole block; after the last window row the
 //     producers read it back (tcgen05.ld) into shared memory in [r][x] order and the consumers pick their 32 values.
+//   * the tensor core TRUNCATES on every accumulation: measured against float64, the raw sum is low by 0.9e-5 .. 4.4e-5
+//     (mean 2.6e-5) after the 525 tcgen05.mma of a 35x35 window and by 1.4e-5 .. 7.9e-5 (mean 5.0e-5) after the 1071 of a
+//     51x51 one, i.e. 4.95e-8 = 0.83 * 2^-24 of the sum per MMA on average.  The epilogue multiplies the denominator by
+//     1 + 4.95e-8 * (MMAs accumulated), which centres the error: +-1.8e-5 at win 35, +-3.6e-5 worst at win 51 (tools/
+//     err_probe.py), inside the 5e-5 cost tolerance.  (Banking partial sums every 8 rows in float32 brought it to 1.2e-5
+//     but cost 24 %: there is no room for a second accumulator in TMEM or shared memory, and red.global runs at 1.3
+//     cycles per lane.)
 //   * TMEM map (512 columns): D half h at 96 h; A at 192 + 160 stage + 80 half + 40 (hi|lo) + j  (win <= 39).
 //     SINGLE (39 < win <= 79): one stage of A, 192 + 2 KC half + KC (hi|lo) + j with KC = 8 ceil(win / 8), and one stage of
 //     the left-weight residual in shared memory; the producers then wait for the previous row's MMAs (a second commit onto
@@ -27,6 +34,7 @@ constexpr int TC_SBO = 144;                       // bytes between 8-column grou
 constexpr int TC_LBO = (TILE_WS / 8) * TC_SBO;    // bytes between the two 4-offset chunks of a K group
 constexpr int TC_KGB = 2 * TC_LBO;                // bytes per K group (8 window offsets)
 constexpr int TC_DS_BYTES = 224 * TILE_WS * 4;    // denominators read back: [r][x]
+constexpr float TC_TRUNC_PER_MMA = 4.95e-8f;      // mean relative truncation loss of the TMEM accumulator per tcgen05.mma
 
 struct TcSmem {
     int e, f1, f2, pa, c1, c2, w1, w2, ds, total;
@@ -423,6 +431,7 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
     const float *Ds = reinterpret_cast<const float *>(smem + sp.ds);
+    const float den_fix = 1.0f + TC_TRUNC_PER_MMA * (float)(3 * KG * nsteps);   // see the header: truncating accumulator
     const int rowo = y - g.row0;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
@@ -436,7 +445,7 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
         for (int b = 0; b < 4; ++b) {
             const int d = dlo + kb + b;
             const bool valid = (x < g.W) && (d <= g.dHi) && (x - d >= 0);
-            const float den = Ds[(T - 1 - (xb + a) + kb + b) * T + xb + a];
+            const float den = __fmul_rn(Ds[(T - 1 - (xb + a) + kb + b) * T + xb + a], den_fix);
             const float cost = __fdiv_rn(c0[b], den);                   // cost / tot (:88)
             out0[b] = valid ? cost : INFINITY;
             if (valid) {
