@@ -381,3 +381,25 @@ def test_c_abi_from_plain_c(tmp_path):
     assert np.array_equal(gsw, ss.passive.StereoGSW(7, 24, 0, 10, 120.0, 3, 20).compute(l, r))
     d = ss.passive.StereoASW(9, 24, 0, 5.0, 17.5, False).compute(l, r)
     assert np.array_equal(pts, ss.points.getAdimensional3DPoints(d), equal_nan=True)
+
+
+def test_tensor_core_and_cuda_core_aggregation_agree(monkeypatch):
+    """ASW with 128-disparity chunks runs k_aggregate_tc (denominators on tcgen05, 3xTF32 + truncation compensation);
+    SS_TCDEN=0 forces the all-CUDA-core k_aggregate_ws.  Same parity bar for both, and they must agree with each other:
+    costs to 5e-5, maps except at near-ties."""
+    l, r, _ = synth_pair(330, 44, 139, 17)
+    for win in (35, 51):                                   # double-staged and single-staged operand variants
+        kw = dict(winSize=win, maxDisparity=139, minDisparity=0, gammaC=9.0, gammaP=25.0, consistent=True)
+        ref = oracle.asw(l, r, stages=True, cost=True, **kw)
+        out = {}
+        for tc in ("1", "0"):
+            monkeypatch.setenv("SS_TCDEN", tc)
+            out[tc] = ss.passive.StereoASW(**kw).compute_staged(l, r, cost=True)
+            parity.check_cost(out[tc]["cost"], ref["cost"])
+            parity.check_staged(out[tc], ref, ref["cost"], ref["cost"], 0, True, max_fraction=0.01)
+        monkeypatch.delenv("SS_TCDEN")
+        fin = np.isfinite(out["0"]["cost"])
+        assert np.array_equal(fin, np.isfinite(out["1"]["cost"]))
+        assert np.allclose(out["1"]["cost"][fin], out["0"]["cost"][fin], rtol=5e-5, atol=1e-5)
+        # where the two maps differ, the two picks are a near-tie of the oracle's own costs
+        parity.adjudicate_left(out["1"]["left"], out["0"]["left"], ref["cost"], 0, max_fraction=None)
