@@ -11,12 +11,15 @@
 //   k_cost_volume     raw per-pixel matching cost E[row][u][d] (truncated AD / capped colour distance,
 //                     _passive.cpp:77-79, :528-531), chunk-major so an aggregation tile is one
 //                     contiguous span that a single TMA bulk copy brings into shared memory.
-//   k_aggregate       the hot kernel (>99 % of the time): per (row, 64-column tile, disparity chunk)
-//                     streams the window rows through shared memory (cp.async.bulk + mbarrier),
-//                     tabulates both support-weight rows once per (pixel, offset) -- the reference
-//                     re-evaluates exp/sqrt/pow for every (x,d) pair, _passive.cpp:71-74 -- and
-//                     accumulates numerator / denominator in registers with packed fma.rn.f32x2
-//                     (FFMA2/FMUL2/FADD2: two lanes' worth of work per issued instruction).
+//   k_aggregate_tc /  the hot kernels (98 % of the time): per (row, 96-column tile, 128-disparity chunk) producer warps
+//   k_aggregate_ws    stream the window rows through shared memory (cp.async.bulk + mbarrier) and tabulate both
+//                     support-weight rows once per (pixel, offset) -- the reference re-evaluates exp/sqrt/pow for every
+//                     (x,d) pair, _passive.cpp:71-74 -- while consumer warps accumulate in registers with packed
+//                     fma.rn.f32x2 (FFMA2/FMUL2/FADD2: two lanes' worth of work per issued instruction).  In
+//                     k_aggregate_tc (ss_aggregate_tc.cuh; ASW, 128-disparity chunks) the denominators run on the
+//                     tensor cores instead: tcgen05.mma kind::tf32, 3xTF32 split, right weights in tensor memory,
+//                     accumulator in TMEM.  k_aggregate_ws is the all-CUDA-core form (GSW, short disparity ranges);
+//                     k_aggregate the older single-role GSW fallback for windows whose float cost tiles do not fit.
 //                     WTA over the disparity chunk is fused (warp shuffle + 64-bit atomicMin keys).
 //   k_wta_right       right-reference WTA: minimum over diagonals of the SAME aggregated volume
 //                     (C_R[xr,d] == C_L[xr+d,d]), so the "roughly doubled" second
