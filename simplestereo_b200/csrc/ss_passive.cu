@@ -135,28 +135,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
 #endif
 }
-// same, for waits that are expected to be long (producers waiting for a free buffer): back off between polls so
-// the polling warp does not take issue slots from the arithmetic warps
-__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
-#ifdef SS_SLEEP_NS
-    uint32_t done = 0;
-    while (true) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
-        __nanosleep(SS_SLEEP_NS);
-    }
-#else
-    mbar_wait(bar, parity);
-#endif
-}
+// waits that are expected to be long (producers waiting for a free buffer) -- same primitive: with the suspend-time hint a
+// waiting warp is parked in hardware, a software back-off (nanosleep) measured no better
+__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 // TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
