@@ -383,6 +383,8 @@ def run_b200(args):
         "kernel": "k_aggregate_tc<ASW, DC=128> (warp-specialised support-weight aggregation + WTA; numerators on packed FP32, denominators on tcgen05 3xTF32)", "kernel_ms": agg_avg_s * 1e3, "kernel_share_of_step": agg_ms / total_ms if world == 1 else None,
         "peak_source": "FFMA-only microbenchmark run live on this GPU (ss_measure_fp32_peak); nominal 74.4 TFLOP/s",
         "algorithmic_flops_per_launch": flops_per_launch,
+        "note": "4 algorithmic flop per window element (mul, fma, add); the add (denominator) runs on the tensor cores "
+                "(tcgen05 kind::tf32, 3xTF32) and is not counted twice; ncu: tensor pipe 11 % active, see profiles/",
         "hbm": {"achieved": bytes_per_launch / agg_avg_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": bytes_per_launch / agg_avg_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch},
