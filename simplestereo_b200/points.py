@@ -140,16 +140,22 @@ def exportPLY(points3D, filepath, referenceImage=None, precision=6):
 
 def importPLY(filename, *properties):
     """
-    Import 3D coordinates from PLY file (reference: simplestereo/points.py:82-121).
+    Read the vertex table of an ASCII PLY file written by ``exportPLY`` (reference: simplestereo/points.py:82-121).
 
-    ``properties``: property column positions to be extracted as float, in the same order (default (0, 1, 2)).
-    Returns an array of shape (number of values, number of properties).
+    ``properties`` selects columns of the vertex lines by position (default 0, 1, 2 = x, y, z); the result is a float
+    array with one row per vertex and one column per requested property, in the requested order.
     """
-    if not properties:
-        properties = (0, 1, 2)
+    cols = properties if properties else (0, 1, 2)
     with open(filename, "r") as f:
-        for line in f:
-            if line.rstrip().lower() == "end_header":
-                break
-        rows = [line.split(" ") for line in f]
-    return np.asarray([[float(r[x]) for x in properties] for r in rows], dtype=float)
+        text = f.read()
+    head, sep, body = text.partition("end_header\n")
+    if not sep:                                   # tolerate other capitalisation / trailing blanks, as the reference does
+        lines = text.splitlines()
+        k = next(i for i, ln in enumerate(lines) if ln.rstrip().lower() == "end_header")
+        body = "\n".join(lines[k + 1:])
+    rows = [ln.split(" ") for ln in body.splitlines()]
+    out = np.empty((len(rows), len(cols)), dtype=float)
+    for i, fields in enumerate(rows):
+        for j, c in enumerate(cols):
+            out[i, j] = float(fields[c])
+    return out
