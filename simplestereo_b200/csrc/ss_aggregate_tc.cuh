@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
 
     if (warp >= CW) {
         // =================================== producers ===================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         const int pw = warp - CW;
         const uint32_t lane_base = (uint32_t)(pw * 32) << 16;       // this warp's quarter of the TMEM lanes
         const int f2_start = x0 - dlo - DC + 1 - pad + g.PL2;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
                 const float4 *nb = f2 + src;
                 float *dst = W2s + col;
                 const uint32_t ta = tbase + lane_base + colA(sw, cb >> 2, 0);
-#pragma unroll 1
+#pragma unroll 2
                 for (int jb = 0; jb < NB; ++jb) {
                     const float4 t = *reinterpret_cast<const float4 *>(parg + 4 * jb);
                     const float4 n0 = nb[0], n1 = nb[1], n2 = nb[2], n3 = nb[3];
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
     }
 
     // =================================== consumers ===================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
     const int xl = lane >> 3, dl = lane & 7;
     const int xg = (warp / NDB) * 4 + xl;
     const int dg = ((warp % NDB) * 8 + dl + 2 * xl) % (DC / 4);
