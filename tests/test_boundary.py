@@ -99,3 +99,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".h", ".cuh", ".cpp")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_headers_are_plain_c():
+    """The boundary is a C ABI: both headers must compile as C (no C++ constructs, no torch / numpy types) and the
+    plain-C caller used on the GPU box must at least parse and link against the declared prototypes."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    for h in ("ss_passive.h", "ss_post.h"):
+        src = f'#include "{os.path.join(ROOT, "include", h)}"\nint main(void) {{ return SS_OK; }}\n' if h == "ss_passive.h" else \
+              f'#include "{os.path.join(ROOT, "include", h)}"\nint main(void) {{ return 0; }}\n'
+        r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", "-"], input=src,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-fsyntax-only", os.path.join(ROOT, "tests", "c_abi_smoke.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
