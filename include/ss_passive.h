@@ -11,11 +11,12 @@
  *   - all functions return SS_OK (0) or a negative SS_ERR_* code; ss_last_error() gives the text.
  *   - "host" entry points take host pointers and do H2D / compute / D2H internally;
  *     "device" entry points take device pointers and a cudaStream_t (passed as void*) and only
- *     enqueue work -- nothing is synchronised.
+ *     enqueue work on the caller's CURRENT device -- nothing is synchronised.  Calls may use different streams: the cached
+ *     scratch is shared per device, so each call's stream first waits (cudaStreamWaitEvent) for the previous call's work.
  *   - rows [row_begin,row_end) select an image-row stripe (rows are independent jobs in the
  *     reference, _passive.cpp:372-374); output buffers of *_rows/_device calls hold only the stripe.
  *   - the library keeps no host pointer after a call returns.  Device scratch is cached per
- *     process and grows on demand (ss_shutdown releases it).
+ *     device and grows on demand (ss_shutdown releases it).  Calls are serialised per device (internal mutex).
  *   - there is no CPU fallback: without a CUDA device every compute call fails with SS_ERR_CUDA.
  */
 #ifndef SS_PASSIVE_H
@@ -39,10 +40,21 @@ extern "C" {
 
 /* ---- process-wide context ------------------------------------------------------------- */
 
-/* Select the CUDA device used by this process (one process per GPU).  Optional: the first
- * compute call initialises device 0 / the current device.  Replaces the reference's thread-pool
- * set-up (std::thread::hardware_concurrency() workers, _passive.cpp:351-355, :751-754). */
+/* Select the CUDA device the host entry points of this process run on (one process per GPU).  Optional: without it
+ * they use the caller's current device.  Replaces the reference's thread-pool set-up
+ * (std::thread::hardware_concurrency() workers, _passive.cpp:351-355, :751-754). */
 int ss_init(int device);
+
+/* Single-process multi-GPU: the host entry points (ss_asw_compute, ss_gsw_compute, *_rows) shard the image rows over
+ * `devices[0..n)` -- one host thread and one context (stream, cached scratch) per device, every device reading the rows it
+ * needs from the caller's arrays and writing its stripe straight into the caller's output, no collective -- exactly the
+ * unit the reference's workers pop from their queue (a row index, _passive.cpp:372-374).  devices == NULL or n <= 0 selects
+ * every visible device.  When n > 1 the NCCL communicators of ss_*_compute_multi_device are created too
+ * (ncclCommInitAll; libnccl.so.2 is loaded at run time and its absence is not an error here).
+ * The device-resident entry points always run on the caller's CURRENT device, whatever this list holds. */
+int ss_init_devices(const int *devices, int n);
+/* number of devices in the list (0 before ss_init / ss_init_devices) */
+int ss_device_count(void);
 
 /* Free every cached device buffer.  (The reference never frees anything, _passive.cpp:338-358.) */
 int ss_shutdown(void);
@@ -91,9 +103,25 @@ int ss_gsw_compute_device(const uint8_t *d_img1, const uint8_t *d_img2, int widt
                           int iterations, int bins, int row_begin, int row_end, int16_t *d_out_rows,
                           void *stream);
 
+/* Single-process multi-GPU, device-resident.  Arrays of n = ss_device_count() pointers, entry k on device k of the
+ * ss_init_devices list: d_img1[k] / d_img2[k] copies of the full images, d_out[k] a buffer of n * ceil(H/n) x W int16
+ * (equal stripes: the all-gather needs them), streams[k] a cudaStream_t of device k (streams == NULL: the library's own
+ * streams, synchronised before returning).  Device k computes rows [k*S, (k+1)*S) into its slot of d_out[k] and ONE
+ * grouped in-place ncclAllGather leaves the whole map on every device. */
+int ss_asw_compute_multi_device(const uint8_t *const *d_img1, const uint8_t *const *d_img2, int width, int height,
+                                int win_size, int max_disp, int min_disp, double gamma_c, double gamma_p, int consistent,
+                                int16_t *const *d_out, void *const *streams);
+int ss_gsw_compute_multi_device(const uint8_t *const *d_img1, const uint8_t *const *d_img2, int width, int height,
+                                int win_size, int max_disp, int min_disp, int gamma, float f_max, int iterations, int bins,
+                                int16_t *const *d_out, void *const *streams);
+
 /* ---- disparity-range sharding (device buffers) ----------------------------------------- */
 
-/* Evaluate only disparities [disp_begin,disp_end] (inclusive, clipped to [min_disp,max_disp]) and
+/* The kernel and its disparity-chunk grid are chosen from the CALL's range [min_disp,max_disp] (chunks start at
+ * min_disp + k * chunk), never from the sub-range: every cost a shard computes is bit-identical to the unsharded call's,
+ * so merged shards reproduce the unsharded map exactly.  Shards aligned to the chunk size (128 disparities when the call
+ * spans more than 64) waste no work.
+ * Evaluate only disparities [disp_begin,disp_end] (inclusive, clipped to [min_disp,max_disp]) and
  * return the per-pixel winners as packed keys  (float_bits(cost) << 32) | disparity  (smaller key
  * wins, which is also the reference's smallest-disparity tie-break, _passive.cpp:90-93):
  *   d_best_left  uint64[rows x W]  left-reference winners  (_passive.cpp:54-98)
@@ -125,12 +153,32 @@ int ss_asw_stages(const uint8_t *img1, const uint8_t *img2, int width, int heigh
                   int win_size, int max_disp, int min_disp, double gamma_c, double gamma_p,
                   int consistent, int16_t *out_left, int16_t *out_right, uint8_t *out_invalid,
                   int16_t *out_final, float *out_cost);
+/* The same for the image-row stripe [row_begin,row_end): every output holds only the stripe's rows (full-size frames are
+ * checked against the oracle a few rows at a time). */
+int ss_asw_stages_rows(const uint8_t *img1, const uint8_t *img2, int width, int height,
+                       int win_size, int max_disp, int min_disp, double gamma_c, double gamma_p,
+                       int consistent, int row_begin, int row_end, int16_t *out_left, int16_t *out_right,
+                       uint8_t *out_invalid, int16_t *out_final, float *out_cost);
+int ss_gsw_stages_rows(const uint8_t *img1, const uint8_t *img2, int width, int height,
+                       int win_size, int max_disp, int min_disp, int gamma, float f_max,
+                       int iterations, int bins, int row_begin, int row_end, int16_t *out_left,
+                       int16_t *out_right, uint8_t *out_invalid, int16_t *out_final,
+                       float *out_cost_left, float *out_cost_right);
 /* GSW: out_cost_left / out_cost_right are the left- and right-reference volumes, both indexed by
  * the LEFT column:  (y*W + x)*D + (disp - min_disp). */
 int ss_gsw_stages(const uint8_t *img1, const uint8_t *img2, int width, int height,
                   int win_size, int max_disp, int min_disp, int gamma, float f_max,
                   int iterations, int bins, int16_t *out_left, int16_t *out_right,
                   uint8_t *out_invalid, int16_t *out_final, float *out_cost_left, float *out_cost_right);
+
+/* BGR -> CIELab exactly as the kernels see it (float32 L,a,b per pixel, H*W*3): the conversion stage of
+ * ColorConversion::ImageFromBGR2Lab (headers/colorconversion.hpp:18-86) on its own, for parity tests. */
+int ss_debug_lab(const uint8_t *img, int width, int height, float *out_lab);
+
+/* Which aggregation kernel served the last call on `device` (< 0: the device of the host entry points): 1 = k_aggregate_tc
+ * (tensor-core denominators), 2 = k_aggregate_ws (all CUDA cores), 0 = none yet; *disp_chunk (may be NULL) receives the
+ * disparity chunk it ran with.  Lets the parity tests assert that a case reached the kernel it is meant to cover. */
+int ss_debug_last_kernel(int device, int *disp_chunk);
 
 /* ---- instrumentation ------------------------------------------------------------------- */
 

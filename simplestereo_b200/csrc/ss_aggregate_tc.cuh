@@ -16,13 +16,17 @@
 //     serves the consumers (one LDS.128 = one column's weights for 4 consecutive window offsets).
 //   * the accumulator (2 x 128 lanes x 96 columns) stays in TMEM for the whole block; after the last window row the
 //     producers read it back (tcgen05.ld) into shared memory in [r][x] order and the consumers pick their 32 values.
-//   * the tensor core TRUNCATES on every accumulation: measured against float64, the raw sum is low by 0.9e-5 .. 4.4e-5
-//     (mean 2.6e-5) after the 525 tcgen05.mma of a 35x35 window and by 1.4e-5 .. 7.9e-5 (mean 5.0e-5) after the 1071 of a
-//     51x51 one, i.e. 4.95e-8 = 0.83 * 2^-24 of the sum per MMA on average.  The epilogue multiplies the denominator by
-//     1 + 4.95e-8 * (MMAs accumulated), which centres the error: +-1.8e-5 at win 35, +-3.6e-5 worst at win 51 (tools/
-//     err_probe.py), inside the 5e-5 cost tolerance.  (Banking partial sums every 8 rows in float32 brought it to 1.2e-5
-//     but cost 24 %: there is no room for a second accumulator in TMEM or shared memory, and red.global runs at 1.3
-//     cycles per lane.)
+//   * the tensor core TRUNCATES on every accumulation: each tcgen05.mma loses at most one ulp of the running sum, so after
+//     n accumulating MMAs the raw denominator is low by a relative 0 .. n * 2^-23 (measured against float64,
+//     profiles/r01d_tc_denominator_error.txt: 0.9e-5 .. 4.4e-5 after the 525 MMAs of a 35x35 window, mean 0.83 * 2^-24 per
+//     MMA).  The epilogue multiplies by 1 + n * 2^-24, the CENTRE of that interval, so |error| <= n * 2^-24 for ANY
+//     input -- a bound, not a fit: 3.1e-5 at win 35 (n = 3 * 5 K-groups * 35 rows), 4.4e-5 at win 41 -- inside the 5e-5 cost
+//     tolerance the tests state.  n counts only MMAs that can add something to this (x, d): window rows inside the image
+//     and K-groups that intersect the pair's valid window columns (adding exact zeros truncates nothing), so border pixels
+//     are not over-compensated.  Windows above TC_MAX_WIN = 41 (ss_passive.cu) would exceed the bound and run
+//     k_aggregate_ws.  (Banking partial sums every 8 rows in float32 would make the bound independent of the window, but
+//     there is no room for a second accumulator in TMEM -- D 192 + operands 160..224 columns of 512 -- and red.global
+//     runs at 1.3 cycles per lane: measured +24 %.)
 //   * TMEM map (512 columns): D half h at 96 h; A at 192 + 160 stage + 80 half + 40 (hi|lo) + j  (win <= 39).
 //     SINGLE (39 < win <= 79): one stage of A, 192 + 2 KC half + KC (hi|lo) + j with KC = 8 ceil(win / 8), and one stage of
 //     the left-weight residual in shared memory; the producers then wait for the previous row's MMAs (a second commit onto
@@ -34,7 +38,7 @@ constexpr int TC_SBO = 144;                       // bytes between 8-column grou
 constexpr int TC_LBO = (TILE_WS / 8) * TC_SBO;    // bytes between the two 4-offset chunks of a K group
 constexpr int TC_KGB = 2 * TC_LBO;                // bytes per K group (8 window offsets)
 constexpr int TC_DS_BYTES = 224 * TILE_WS * 4;    // denominators read back: [r][x]
-constexpr float TC_TRUNC_PER_MMA = 4.95e-8f;      // mean relative truncation loss of the TMEM accumulator per tcgen05.mma
+constexpr float TC_TRUNC_PER_MMA = 5.9604645e-8f;  // 2^-24: half the worst-case relative truncation loss of one tcgen05.mma
 
 struct TcSmem {
     int e, f1, f2, pa, c1, c2, w1, w2, ds, total;
@@ -198,16 +202,16 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
             const int st = n & 1, ph = (n >> 1) & 1;
             if (pw == 0 && lane == 0) {
                 if (n + 1 < nsteps) {
-                    mbar_wait_long(BAR(3 + ((n + 1) & 1)), (((n + 1) >> 1) & 1) ^ 1);
+                    mbar_wait(BAR(3 + ((n + 1) & 1)), (((n + 1) >> 1) & 1) ^ 1);
                     issue_F(n + 1);
                 }
-                mbar_wait_long(BAR(13 + st), ph ^ 1);
+                mbar_wait(BAR(13 + st), ph ^ 1);
                 issue_E(n);
             }
             __syncwarp();
             if (n == 0) mbar_wait(BAR(0), 0);
             mbar_wait(BAR(1 + st), ph);            // features of this window row have landed
-            mbar_wait_long(BAR(8 + sw), phw ^ 1);  // consumers AND the tensor core are done with this weight stage
+            mbar_wait(BAR(8 + sw), phw ^ 1);  // consumers AND the tensor core are done with this weight stage
             if (SINGLE && n > 0) mbar_wait(BAR(7), (n - 1) & 1);   // single-stage operands: the previous row's MMAs have read them
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
     const int xg = (warp / NDB) * 4 + xl;
     const int dg = ((warp % NDB) * 8 + dl + 2 * xl) % (DC / 4);
     const int xb = 8 * xg, kb = 4 * dg;
-    const bool lane_live = (x0 + xb < g.W) && (dlo + kb <= g.dHi) && (x0 + xb + 7 >= dlo + kb);
+    const bool lane_live = (x0 + xb < g.W) && (dlo + kb <= g.dHi) && (dlo + kb + 3 >= g.dVLo) && (x0 + xb + 7 >= dlo + kb);
     const bool warp_live = __any_sync(0xffffffffu, lane_live);
     const int R0 = T - 8 - xb + kb;
 
@@ -430,8 +434,8 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
     mbar_wait(BAR(15), 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512));
-    const float *Ds = reinterpret_cast<const float *>(smem + sp.ds);
-    const float den_fix = 1.0f + TC_TRUNC_PER_MMA * (float)(3 * KG * nsteps);   // see the header: truncating accumulator
+    float *Ds = reinterpret_cast<float *>(smem + sp.ds);
+    const float fix_kg = TC_TRUNC_PER_MMA * (float)(3 * nsteps);   // per K-group that contributes; see the header
     const int rowo = y - g.row0;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
@@ -444,14 +448,18 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int d = dlo + kb + b;
-            const bool valid = (x < g.W) && (d <= g.dHi) && (x - d >= 0);
-            const float den = __fmul_rn(Ds[(T - 1 - (xb + a) + kb + b) * T + xb + a], den_fix);
+            const bool valid = (x < g.W) && (d >= g.dVLo) && (d <= g.dHi) && (x - d >= 0);
+            float *dp = Ds + (T - 1 - (xb + a) + kb + b) * T + xb + a;
+            // valid window columns of this pair: right column x-d-pad+j >= 0 and left column x-pad+j < W (_passive.cpp:67-68)
+            const int jlo = max(0, pad - (x - d)), jhi = min(win - 1, g.W - 1 - x + pad);
+            const float den = __fmul_rn(*dp, fmaf(fix_kg, (float)((jhi >> 3) - (jlo >> 3) + 1), 1.0f));
             const float cost = __fdiv_rn(c0[b], den);                   // cost / tot (:88)
             out0[b] = valid ? cost : INFINITY;
             if (valid) {
                 const u64 k = make_key(cost, d);
                 best = k < best ? k : best;
             }
+            if (P.bestR) *dp = out0[b];          // in place: the slot of den[x][d] now holds cost[x][d] (right-reference WTA below)
         }
 #pragma unroll
         for (int off = 1; off < 8; off <<= 1) {
@@ -463,5 +471,9 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
             const size_t o = ((size_t)rowo * g.W + x) * P.Dp + (size_t)ch * DC + kb;
             *reinterpret_cast<float4 *>(P.vol0 + o) = make_float4(out0[0], out0[1], out0[2], out0[3]);
         }
+    }
+    if (P.bestR) {
+        asm volatile("bar.sync 2, %0;" ::"n"(CW * 32) : "memory");
+        wta_right_rows<T, DC>(Ds, warp, CW, lane, x0, dlo, g.W, P.bestR + (size_t)rowo * g.W);
     }
 }

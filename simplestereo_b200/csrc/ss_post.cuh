@@ -205,9 +205,9 @@ int ss_reproject_device(const int16_t *d_disp, int width, int height, const doub
     if (!d_disp || !Q || !d_points) return fail(SS_ERR_FORMAT, "Invalid input format!");
     int rc = post_check_dims(width, height);
     if (rc) return rc;
-    Ctx &c = g_ctx;
-    std::lock_guard<std::mutex> lk(c.mu);
-    if ((rc = ctx_init(-1))) return rc;
+    CtxLock L(current_device());
+    if (L.rc) return L.rc;
+    Ctx &c = *L.c;
     return post_reproject_enqueue(c, d_disp, width, height, Q, d_points, (cudaStream_t)stream);
 }
 
@@ -215,17 +215,18 @@ int ss_reproject(const int16_t *disp, int width, int height, const double *Q, fl
     if (!disp || !Q || !points) return fail(SS_ERR_FORMAT, "Invalid input format!");
     int rc = post_check_dims(width, height);
     if (rc) return rc;
-    Ctx &c = g_ctx;
-    std::lock_guard<std::mutex> lk(c.mu);
-    if ((rc = ctx_init(-1))) return rc;
-    CU_TRY(cudaSetDevice(c.device));
+    CtxLock L(default_device());
+    if (L.rc) return L.rc;
+    Ctx &c = *L.c;
     const size_t n = (size_t)width * height;
     if ((rc = ensure(c.out, n * 2 + 2))) return rc;
     if ((rc = ensure(c.post_pts, n * 12))) return rc;
     cudaStream_t st = c.stream;
+    if ((rc = scratch_begin(c, st))) return rc;
     CU_TRY(cudaMemcpyAsync(c.out.p, disp, n * 2, cudaMemcpyHostToDevice, st));
     if ((rc = post_reproject_enqueue(c, (const int16_t *)c.out.p, width, height, Q, (float *)c.post_pts.p, st))) return rc;
     CU_TRY(cudaMemcpyAsync(points, c.post_pts.p, n * 12, cudaMemcpyDeviceToHost, st));
+    if ((rc = scratch_end(c, st))) return rc;
     CU_TRY(cudaStreamSynchronize(st));
     return SS_OK;
 }
@@ -237,16 +238,16 @@ int ss_asw_compute_points(const uint8_t *img1, const uint8_t *img2, int width, i
     const Call q = asw_call(width, height, win_size, max_disp, min_disp, gamma_c, gamma_p, consistent, 0, height);
     int rc = validate(q);
     if (rc) return rc;
-    Ctx &c = g_ctx;
-    std::lock_guard<std::mutex> lk(c.mu);
-    if ((rc = ctx_init(-1))) return rc;
-    CU_TRY(cudaSetDevice(c.device));
+    CtxLock L(default_device());
+    if (L.rc) return L.rc;
+    Ctx &c = *L.c;
     const size_t nimg = (size_t)width * height * 3, npx = (size_t)width * height;
     if ((rc = ensure(c.img1, nimg))) return rc;
     if ((rc = ensure(c.img2, nimg))) return rc;
     if ((rc = ensure(c.out, npx * 2 + 2))) return rc;
     if ((rc = ensure(c.post_pts, npx * 12))) return rc;
     cudaStream_t st = c.stream;
+    if ((rc = scratch_begin(c, st))) return rc;
     CU_TRY(cudaMemcpyAsync(c.img1.p, img1, nimg, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(c.img2.p, img2, nimg, cudaMemcpyHostToDevice, st));
     Outputs o;
@@ -256,6 +257,7 @@ int ss_asw_compute_points(const uint8_t *img1, const uint8_t *img2, int width, i
     if ((rc = post_reproject_enqueue(c, (const int16_t *)c.out.p, width, height, Q, (float *)c.post_pts.p, st))) return rc;
     if (out_disp) CU_TRY(cudaMemcpyAsync(out_disp, c.out.p, npx * 2, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(out_points, c.post_pts.p, npx * 12, cudaMemcpyDeviceToHost, st));
+    if ((rc = scratch_end(c, st))) return rc;
     CU_TRY(cudaStreamSynchronize(st));
     return SS_OK;
 }
@@ -265,30 +267,33 @@ int ss_normalize_colormap_device(const int16_t *d_disp, int width, int height, c
     if (!d_disp || !d_lut_bgr || (!d_gray && !d_bgr)) return fail(SS_ERR_FORMAT, "Invalid input format!");
     int rc = post_check_dims(width, height);
     if (rc) return rc;
-    Ctx &c = g_ctx;
-    std::lock_guard<std::mutex> lk(c.mu);
-    if ((rc = ctx_init(-1))) return rc;
-    return post_colormap_enqueue(c, d_disp, width, height, d_lut_bgr, d_gray, d_bgr, (cudaStream_t)stream);
+    CtxLock L(current_device());
+    if (L.rc) return L.rc;
+    Ctx &c = *L.c;
+    if ((rc = scratch_begin(c, (cudaStream_t)stream))) return rc;
+    if ((rc = post_colormap_enqueue(c, d_disp, width, height, d_lut_bgr, d_gray, d_bgr, (cudaStream_t)stream))) return rc;
+    return scratch_end(c, (cudaStream_t)stream);
 }
 
 int ss_normalize_colormap(const int16_t *disp, int width, int height, const uint8_t *lut_bgr, uint8_t *gray, uint8_t *bgr) {
     if (!disp || !lut_bgr || (!gray && !bgr)) return fail(SS_ERR_FORMAT, "Invalid input format!");
     int rc = post_check_dims(width, height);
     if (rc) return rc;
-    Ctx &c = g_ctx;
-    std::lock_guard<std::mutex> lk(c.mu);
-    if ((rc = ctx_init(-1))) return rc;
-    CU_TRY(cudaSetDevice(c.device));
+    CtxLock L(default_device());
+    if (L.rc) return L.rc;
+    Ctx &c = *L.c;
     const size_t n = (size_t)width * height;
     if ((rc = ensure(c.out, n * 2 + 2))) return rc;
     if ((rc = ensure(c.post_a, n * 4 + 768 + 8))) return rc;      // [lut 768 | bgr 3n, padded to 4 | gray n]
     cudaStream_t st = c.stream;
+    if ((rc = scratch_begin(c, st))) return rc;
     uint8_t *d_lut = (uint8_t *)c.post_a.p, *d_bgr = d_lut + 768, *d_gray = d_bgr + ((3 * n + 3) & ~(size_t)3);
     CU_TRY(cudaMemcpyAsync(c.out.p, disp, n * 2, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_lut, lut_bgr, 768, cudaMemcpyHostToDevice, st));
     if ((rc = post_colormap_enqueue(c, (const int16_t *)c.out.p, width, height, d_lut, d_gray, d_bgr, st))) return rc;
     if (gray) CU_TRY(cudaMemcpyAsync(gray, d_gray, n, cudaMemcpyDeviceToHost, st));
     if (bgr) CU_TRY(cudaMemcpyAsync(bgr, d_bgr, 3 * n, cudaMemcpyDeviceToHost, st));
+    if ((rc = scratch_end(c, st))) return rc;
     CU_TRY(cudaStreamSynchronize(st));
     return SS_OK;
 }
@@ -299,9 +304,9 @@ int ss_remap_linear_device(const uint8_t *d_src, int src_width, int src_height, 
     int rc = post_check_dims(src_width, src_height);
     if (rc) return rc;
     if ((rc = post_check_dims(dst_width, dst_height))) return rc;
-    Ctx &c = g_ctx;
-    std::lock_guard<std::mutex> lk(c.mu);
-    if ((rc = ctx_init(-1))) return rc;
+    CtxLock L(current_device());
+    if (L.rc) return L.rc;
+    Ctx &c = *L.c;
     dim3 b(128), g((dst_width + 127) / 128, dst_height);
     k_remap_linear<<<g, b, 0, (cudaStream_t)stream>>>(d_src, src_width, src_height, d_mapx, d_mapy, dst_width, dst_height, d_dst);
     CU_TRY(cudaGetLastError());
@@ -315,15 +320,15 @@ int ss_remap_linear(const uint8_t *src, int src_width, int src_height, const flo
     int rc = post_check_dims(src_width, src_height);
     if (rc) return rc;
     if ((rc = post_check_dims(dst_width, dst_height))) return rc;
-    Ctx &c = g_ctx;
-    std::lock_guard<std::mutex> lk(c.mu);
-    if ((rc = ctx_init(-1))) return rc;
-    CU_TRY(cudaSetDevice(c.device));
+    CtxLock L(default_device());
+    if (L.rc) return L.rc;
+    Ctx &c = *L.c;
     const size_t ns = (size_t)src_width * src_height * 3, nd = (size_t)dst_width * dst_height;
     if ((rc = ensure(c.img1, ns))) return rc;
     if ((rc = ensure(c.post_pts, nd * 8))) return rc;             // mapx | mapy
     if ((rc = ensure(c.post_a, nd * 3))) return rc;
     cudaStream_t st = c.stream;
+    if ((rc = scratch_begin(c, st))) return rc;
     float *d_mx = (float *)c.post_pts.p, *d_my = d_mx + nd;
     CU_TRY(cudaMemcpyAsync(c.img1.p, src, ns, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_mx, mapx, nd * 4, cudaMemcpyHostToDevice, st));
@@ -334,6 +339,7 @@ int ss_remap_linear(const uint8_t *src, int src_width, int src_height, const flo
     CU_TRY(cudaGetLastError());
     c.total_launches += 1;
     CU_TRY(cudaMemcpyAsync(dst, c.post_a.p, nd * 3, cudaMemcpyDeviceToHost, st));
+    if ((rc = scratch_end(c, st))) return rc;
     CU_TRY(cudaStreamSynchronize(st));
     return SS_OK;
 }

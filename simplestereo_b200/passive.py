@@ -12,8 +12,11 @@ Differences from the reference, all strict supersets of its behaviour (SURVEY.md
   * ``img2`` dtype is checked too (the reference tests ``img1`` twice, _passive.cpp:309);
   * ``gammaC``/``gammaP``/``gamma`` <= 0 and ``minDisparity`` < 0 raise ``ValueError`` instead of
     producing NaN costs / out-of-row reads;
-  * two optional extras: ``rows=(r0, r1)`` computes an image-row stripe, and ``StereoASW.compute_staged`` /
-    ``StereoGSW.compute_staged`` expose the intermediate maps and cost volumes used by the parity tests.
+  * three optional extras: ``rows=(r0, r1)`` computes an image-row stripe; ``devices=[0, 1, ...]`` (constructor keyword,
+    ``"all"`` for every visible GPU) shards the image rows of ``compute`` over several GPUs inside this process --
+    ``ss_init_devices``: one host thread and one context per GPU, no torch, no collective, bit-identical to one GPU; and
+    ``StereoASW.compute_staged`` / ``StereoGSW.compute_staged`` expose the intermediate maps and cost volumes used by
+    the parity tests.
 """
 import numpy as np
 
@@ -65,12 +68,15 @@ class StereoASW():
         Proximity parameter. Default is 17.5.
     consistent : bool
         If True the right-reference pass, left-right check and occlusion filling of the reference
-        (_passive.cpp:191-285) are applied.  On the GPU this costs one extra read of the aggregated
-        cost volume, not a second aggregation.
+        (_passive.cpp:191-285) are applied.  On the GPU the right-reference WTA is fused into the
+        aggregation launch (one shared-memory pass over the block's costs), not a second aggregation.
+    devices : None, "all" or a sequence of CUDA device indices (keyword only, not in the reference)
+        Shard the image rows of ``compute`` over these GPUs inside this process (``ss_init_devices``).
     """
-    def __init__(self, winSize=35, maxDisparity=16, minDisparity=0, gammaC=5, gammaP=17.5, consistent=False):
+    def __init__(self, winSize=35, maxDisparity=16, minDisparity=0, gammaC=5, gammaP=17.5, consistent=False, *, devices=None):
         if not (winSize > 0 and winSize % 2 == 1):
             raise ValueError("winSize must be a positive odd number!")
+        self.devices = devices
         self.winSize = winSize
         self.maxDisparity = maxDisparity
         self.minDisparity = minDisparity
@@ -92,6 +98,7 @@ class StereoASW():
         img1, img2 = _check_images(img1, img2)
         h, w, _ = img1.shape
         L = _cabi.lib()
+        _cabi.use_devices(self.devices)
         if rows is None:
             out = np.empty((h, w), np.int16)
             _cabi.check(L.ss_asw_compute(_cabi.ptr(img1), _cabi.ptr(img2), w, h, *self._args(), _cabi.ptr(out)))
@@ -101,18 +108,21 @@ class StereoASW():
             _cabi.check(L.ss_asw_compute_rows(_cabi.ptr(img1), _cabi.ptr(img2), w, h, *self._args(), r0, r1, _cabi.ptr(out)))
         return out
 
-    def compute_staged(self, img1, img2, cost=False):
-        """dict(left, right, invalid, final[, cost]) -- the staged outputs of SURVEY.md 8(c)."""
+    def compute_staged(self, img1, img2, cost=False, rows=None):
+        """dict(left, right, invalid, final[, cost]) -- the staged outputs of SURVEY.md 8(c), for the whole frame or for the
+        image-row stripe ``rows=(r0, r1)`` (every array then holds only the stripe's rows)."""
         img1, img2 = _check_images(img1, img2)
         h, w, _ = img1.shape
         win, maxd, mind, gc, gp, cons = self._args()
+        r0, r1 = (0, h) if rows is None else (int(rows[0]), int(rows[1]))
+        n = max(r1 - r0, 0)
         D = max(maxd - mind + 1, 0)
-        o = {"left": np.zeros((h, w), np.int16), "right": np.zeros((h, w), np.int16),
-             "invalid": np.zeros((h, w), np.uint8), "final": np.zeros((h, w), np.int16)}
-        vol = np.full((h, w, D), np.inf, np.float32) if cost else None
-        _cabi.check(_cabi.lib().ss_asw_stages(_cabi.ptr(img1), _cabi.ptr(img2), w, h, win, maxd, mind, gc, gp, cons,
-                                              _cabi.ptr(o["left"]), _cabi.ptr(o["right"]), _cabi.ptr(o["invalid"]),
-                                              _cabi.ptr(o["final"]), _cabi.ptr(vol) if (cost and D > 0) else None))
+        o = {"left": np.zeros((n, w), np.int16), "right": np.zeros((n, w), np.int16),
+             "invalid": np.zeros((n, w), np.uint8), "final": np.zeros((n, w), np.int16)}
+        vol = np.full((n, w, D), np.inf, np.float32) if cost else None
+        _cabi.check(_cabi.lib().ss_asw_stages_rows(_cabi.ptr(img1), _cabi.ptr(img2), w, h, win, maxd, mind, gc, gp, cons, r0, r1,
+                                                   _cabi.ptr(o["left"]), _cabi.ptr(o["right"]), _cabi.ptr(o["invalid"]),
+                                                   _cabi.ptr(o["final"]), _cabi.ptr(vol) if (cost and D > 0) else None))
         if cost:
             o["cost"] = vol
         return o
@@ -135,9 +145,10 @@ class StereoGSW():
     bins : int, optional (unused, as upstream)
     """
     def __init__(self, winSize=11, maxDisparity=16, minDisparity=0, gamma=10,
-                 fMax=120, iterations=3, bins=20):
+                 fMax=120, iterations=3, bins=20, *, devices=None):
         if not (winSize > 0 and winSize % 2 == 1):
             raise ValueError("winSize must be a positive odd number!")
+        self.devices = devices
         self.winSize = winSize
         self.gamma = gamma
         self.maxDisparity = maxDisparity
@@ -155,6 +166,7 @@ class StereoGSW():
         img1, img2 = _check_images(img1, img2)
         h, w, _ = img1.shape
         L = _cabi.lib()
+        _cabi.use_devices(self.devices)
         if rows is None:
             out = np.empty((h, w), np.int16)
             _cabi.check(L.ss_gsw_compute(_cabi.ptr(img1), _cabi.ptr(img2), w, h, *self._args(), _cabi.ptr(out)))
@@ -164,19 +176,21 @@ class StereoGSW():
             _cabi.check(L.ss_gsw_compute_rows(_cabi.ptr(img1), _cabi.ptr(img2), w, h, *self._args(), r0, r1, _cabi.ptr(out)))
         return out
 
-    def compute_staged(self, img1, img2, cost=False):
+    def compute_staged(self, img1, img2, cost=False, rows=None):
         img1, img2 = _check_images(img1, img2)
         h, w, _ = img1.shape
         args = self._args()
+        r0, r1 = (0, h) if rows is None else (int(rows[0]), int(rows[1]))
+        n = max(r1 - r0, 0)
         D = max(args[1] - args[2] + 1, 0)
-        o = {"left": np.zeros((h, w), np.int16), "right": np.zeros((h, w), np.int16),
-             "invalid": np.zeros((h, w), np.uint8), "final": np.zeros((h, w), np.int16)}
-        vl = np.full((h, w, D), np.inf, np.float32) if cost else None
-        vr = np.full((h, w, D), np.inf, np.float32) if cost else None
+        o = {"left": np.zeros((n, w), np.int16), "right": np.zeros((n, w), np.int16),
+             "invalid": np.zeros((n, w), np.uint8), "final": np.zeros((n, w), np.int16)}
+        vl = np.full((n, w, D), np.inf, np.float32) if cost else None
+        vr = np.full((n, w, D), np.inf, np.float32) if cost else None
         on = cost and D > 0
-        _cabi.check(_cabi.lib().ss_gsw_stages(_cabi.ptr(img1), _cabi.ptr(img2), w, h, *args,
-                                              _cabi.ptr(o["left"]), _cabi.ptr(o["right"]), _cabi.ptr(o["invalid"]),
-                                              _cabi.ptr(o["final"]), _cabi.ptr(vl) if on else None, _cabi.ptr(vr) if on else None))
+        _cabi.check(_cabi.lib().ss_gsw_stages_rows(_cabi.ptr(img1), _cabi.ptr(img2), w, h, *args, r0, r1,
+                                                   _cabi.ptr(o["left"]), _cabi.ptr(o["right"]), _cabi.ptr(o["invalid"]),
+                                                   _cabi.ptr(o["final"]), _cabi.ptr(vl) if on else None, _cabi.ptr(vr) if on else None))
         if cost:
             o["cost_left"], o["cost_right"] = vl, vr
         return o

@@ -30,7 +30,7 @@ int main(int argc, char **argv) {
     unsigned char *l = slurp(argv[1], npx * 3), *r = slurp(argv[2], npx * 3);
     int16_t *disp = malloc(npx * 2);
     float *pts = malloc(npx * 12);
-    if (ss_abi_version() != 1) return 3;
+    if (ss_abi_version() != 2) return 3;
     CHECK(ss_init(0));
     CHECK(ss_asw_compute(l, r, W, H, 9, 24, 0, 5.0, 17.5, 1, disp));
     dump(argv[5], ".asw.i16", disp, npx * 2);

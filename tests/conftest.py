@@ -28,3 +28,18 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Per-case parity statistics collected by the GPU tests (tests/parity.py:record) -> gpurun_out/parity_report.json."""
+    try:
+        from tests import parity
+    except Exception:
+        return
+    if not parity.REPORT:
+        return
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_report.json"), "w") as f:
+        json.dump(parity.REPORT, f, indent=1, sort_keys=True)

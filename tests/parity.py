@@ -27,13 +27,26 @@ MAX_TOTAL_FRACTION = 2e-2
 SATURATION = 40.0       # ASW truncation level (_passive.cpp:77); None disables the split
 
 
+REPORT = {}             # per-case parity statistics, written to gpurun_out/parity_report.json at session end (conftest.py)
+
+
+def record(name, **stats):
+    REPORT.setdefault(name, {}).update({k: (float(v) if isinstance(v, (np.floating, float)) else int(v) if isinstance(v, (np.integer, int)) else v)
+                                        for k, v in stats.items()})
+
+
 def check_cost(gpu_cost, ref_cost, what="cost"):
+    """Cost volumes agree to COST_RTOL / COST_ATOL on every evaluated pair.  Returns the largest relative error."""
     fin_g, fin_r = np.isfinite(gpu_cost), np.isfinite(ref_cost)
     assert np.array_equal(fin_g, fin_r), f"{what}: evaluated (x,d) sets differ"
     g, r = gpu_cost[fin_r].astype(np.float64), ref_cost[fin_r].astype(np.float64)
-    if g.size:
-        err = np.abs(g - r) - (COST_ATOL + COST_RTOL * np.abs(r))
-        assert (err <= 0).all(), f"{what}: max excess {err.max():.3e} (max rel {np.max(np.abs(g - r) / np.maximum(np.abs(r), 1e-30)):.3e})"
+    if not g.size:
+        return 0.0
+    err = np.abs(g - r) - (COST_ATOL + COST_RTOL * np.abs(r))
+    max_rel = float(np.max(np.abs(g - r) / np.maximum(np.abs(r), 1e-30)))
+    assert (err <= 0).all(), f"{what}: max excess {err.max():.3e} (max rel {max_rel:.3e})"
+    big = np.abs(r) > 1e-3                       # relative error where it is meaningful
+    return float(np.max(np.abs(g[big] - r[big]) / np.abs(r[big]))) if big.any() else 0.0
 
 
 def _limit(n_unsat, n_all, size, max_fraction, what, saturation):

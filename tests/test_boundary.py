@@ -28,7 +28,7 @@ def test_header_symbols_are_exported():
     lib = ctypes.CDLL(_cabi.LIB_PATH)
     for s in declared:
         assert hasattr(lib, s), f"{s} not exported by libsspassive.so"
-    assert _cabi.lib().ss_abi_version() == 1
+    assert _cabi.lib().ss_abi_version() == 2
 
 
 def test_library_is_sm100a_and_uses_tma_and_packed_fp32():

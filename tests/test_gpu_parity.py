@@ -25,20 +25,47 @@ def test_library_is_the_cuda_one():
     assert _cabi.lib().ss_init(0) == 0
 
 
+def _stripe_parity(name, l, r, kw, rows, expect_kernel=None, max_fraction=parity.MAX_MISMATCH_FRACTION):
+    """Staged maps + cost volume of an image-row stripe against the oracle; records the statistics for profiles/."""
+    from simplestereo_b200 import _cabi
+    cons = bool(kw.get("consistent", False))
+    gpu = ss.passive.StereoASW(**kw).compute_staged(l, r, cost=True, rows=rows)
+    kern, chunk = _cabi.last_kernel()
+    if expect_kernel is not None:
+        assert kern == expect_kernel, f"{name}: served by {kern} (chunk {chunk}), expected {expect_kernel}"
+    ref = oracle.asw(l, r, stages=True, cost=True, rows=rows, **kw)
+    sl = slice(*rows)
+    rr = {k: ref[k][sl] for k in ("left", "right", "invalid", "final")}
+    rel = parity.check_cost(gpu["cost"], ref["cost"], name)
+    nl, nr = parity.check_staged(gpu, rr, ref["cost"], ref["cost"], kw["minDisparity"], cons, max_fraction)
+    parity.record(name, kernel=kern, chunk=chunk, pixels=int(gpu["left"].size), left_mismatch=nl, right_mismatch=nr,
+                  max_rel_cost_err=rel, final_identical=bool(np.array_equal(gpu["final"], rr["final"])))
+    return gpu, ref, nl, nr
+
+
 def test_tsukuba_known_answer_image():
-    """The reference's own golden image (examples/res/tsukuba/disparityASW.png), via examples/010:44-45."""
+    """The reference's own golden image (examples/res/tsukuba/disparityASW.png), via examples/010:44-45.
+    Exact, or -- float32 sums against the reference's float64 -- differing only in the pixels listed in
+    tests/golden/kat_adjudicated.json, each of which is a near-tie of the reference's own float64 costs."""
+    import json
     import cv2
     l, r = cases.load_inputs(("tsukuba", None))
     d = ss.passive.StereoASW(35, 16, 0, 17.5, 17.5, False).compute(l, r)
     assert d.dtype == np.int16 and d.shape == l.shape[:2]
     img = cv2.applyColorMap(cv2.normalize(d, None, 0, 255, cv2.NORM_MINMAX, dtype=cv2.CV_8UC1), cv2.COLORMAP_JET)
     kat = cv2.imread(os.path.join(cases.HERE, "disparityASW.png"))
-    nbad = int((img != kat).any(axis=2).sum())
-    if nbad:
-        # any differing pixel must be a float32 near-tie of the float64 reference costs
+    nbad_img = int((img != kat).any(axis=2).sum())
+    bad = np.argwhere(d != GOLD["asw_tsukuba_kat"])
+    got = sorted([int(y), int(x), int(d[y, x]), int(GOLD["asw_tsukuba_kat"][y, x])] for y, x in bad)
+    print(f"Tsukuba KAT: {len(got)} of {d.size} disparities differ from the reference, {nbad_img} pixels of the golden PNG: {got}")
+    parity.record("tsukuba_kat", pixels=int(d.size), left_mismatch=len(got), png_pixels_differing=nbad_img, list=got)
+    if got:
         ref = oracle.asw(l, r, 35, 16, 0, 17.5, 17.5, False, stages=True, cost=True)
         parity.adjudicate_left(d, GOLD["asw_tsukuba_kat"], ref["cost"], 0)
-    assert nbad <= 0.001 * d.size
+        allowed = json.load(open(os.path.join(cases.HERE, "kat_adjudicated.json")))["pixels"]
+        assert all(g in allowed for g in got), f"pixels outside tests/golden/kat_adjudicated.json: {[g for g in got if g not in allowed]}"
+    else:
+        assert nbad_img == 0
 
 
 @pytest.mark.parametrize("name,spec,kw", cases.ASW_CASES, ids=[c[0] for c in cases.ASW_CASES])
@@ -135,12 +162,10 @@ def c2_full(c2_pair):
 
 def test_c2_stripe_against_oracle(c2_pair, c2_full):
     l, r, _ = c2_pair
-    rows = (180, 192)
-    ref = oracle.asw(l, r, consistent=True, stages=True, cost=True, rows=rows, **C2)
-    sl = slice(*rows)
-    g = {k: c2_full[k][sl] for k in ("left", "right", "invalid", "final")}
-    rr = {k: ref[k][sl] for k in ("left", "right", "invalid", "final")}
-    parity.check_staged(g, rr, ref["cost"], ref["cost"], 0, True)
+    for rows in ((0, 4), (180, 192), (371, 375)):
+        gpu, ref, nl, nr = _stripe_parity(f"c2_rows{rows[0]}", l, r, dict(consistent=True, **C2), rows, expect_kernel="tc")
+        for k in ("left", "right", "invalid", "final"):            # the stripe call is the full-frame call, bit for bit
+            assert np.array_equal(gpu[k], c2_full[k][slice(*rows)])
 
 
 def test_c2_row_stripes_equal_full_frame(c2_pair, c2_full):
@@ -184,13 +209,64 @@ def test_c4_shape_win51_d256_stripe():
     """Middlebury-full parameters (win 51, 256 disparities, L-R) on a full-width band."""
     l, r, _ = synth_pair(2880, 72, 255, 2)
     kw = dict(winSize=51, maxDisparity=255, minDisparity=0, gammaC=5, gammaP=17.5, consistent=True)
-    gpu = ss.passive.StereoASW(**kw).compute_staged(l, r)
-    rows = (34, 37)
-    ref = oracle.asw(l, r, stages=True, cost=True, rows=rows, **kw)
-    sl = slice(*rows)
-    g = {k: gpu[k][sl] for k in ("left", "right", "invalid", "final")}
-    rr = {k: ref[k][sl] for k in ("left", "right", "invalid", "final")}
-    parity.check_staged(g, rr, ref["cost"], ref["cost"], 0, True)
+    _stripe_parity("c4_shape_band_win51_d256", l, r, kw, (34, 37), expect_kernel="ws")
+
+
+# ---- the tensor-core kernel (k_aggregate_tc) on real images, at borders, and at its precision bound ----------------
+
+@pytest.mark.parametrize("win,gc", [(35, 5.0), (35, 17.5), (41, 5.0)])
+def test_tensor_core_kernel_on_tsukuba(win, gc):
+    """Tsukuba with 128 candidates reaches k_aggregate_tc (its 17-candidate default runs 32-disparity chunks on
+    k_aggregate_ws): real texture, real occlusions, sharp colour edges -- both operand-staging variants (win <= 39 / 41)."""
+    l, r = cases.load_inputs(("tsukuba", None))
+    kw = dict(winSize=win, maxDisparity=127, minDisparity=0, gammaC=gc, gammaP=17.5, consistent=True)
+    for rows in ((0, 6), (136, 148), (282, 288)):                     # top border, interior, bottom border
+        _stripe_parity(f"tsukuba_d128_win{win}_gc{gc}_rows{rows[0]}", l, r, kw, rows, expect_kernel="tc")
+
+
+def test_tensor_core_kernel_at_image_borders():
+    """Images barely wider than one tile / narrower than the window: every K-group pattern of the truncation
+    compensation (window columns clipped left, right, both) and clipped window rows, full cost-volume check."""
+    for (w, h, maxd, mind, win, seed) in ((150, 30, 100, 0, 35, 31), (97, 20, 90, 2, 41, 32), (40, 12, 70, 0, 35, 33), (300, 9, 200, 5, 21, 34)):
+        l, r, _ = synth_pair(w, h, maxd, seed)
+        kw = dict(winSize=win, maxDisparity=maxd, minDisparity=mind, gammaC=5.0, gammaP=17.5, consistent=True)
+        _stripe_parity(f"border_{w}x{h}_d{maxd}_win{win}", l, r, kw, (0, h), expect_kernel="tc", max_fraction=0.01)
+
+
+def test_tensor_core_denominator_bound_on_isolated_pixels():
+    """Salt-and-pepper pairs: a pixel unlike all its neighbours has den = 1 + tiny, the MMAs add (almost) nothing and lose
+    nothing, so the centred compensation is at its worst (+n * 2^-24); sparse texture on black the other extreme."""
+    rng = np.random.default_rng(77)
+    for name, p in (("salt", 0.5), ("sparse", 0.03)):
+        l = (rng.random((24, 200, 1)) < p).astype(np.uint8).repeat(3, 2) * 255
+        r = np.roll(l, -7, axis=1)
+        kw = dict(winSize=35, maxDisparity=90, minDisparity=0, gammaC=5.0, gammaP=17.5, consistent=False)
+        _stripe_parity(f"isolated_{name}", l, r, kw, (0, 24), expect_kernel="tc", max_fraction=None)
+
+
+def test_large_windows_run_the_cuda_core_kernel():
+    """win 51 / 63 / 79: beyond the window range whose tensor-core truncation bound fits the tolerance (TC_MAX_WIN = 41)."""
+    l, r, _ = synth_pair(260, 16, 130, 41)
+    for win in (51, 63, 79):
+        kw = dict(winSize=win, maxDisparity=130, minDisparity=0, gammaC=7.0, gammaP=30.0, consistent=True)
+        _stripe_parity(f"large_window_win{win}", l, r, kw, (4, 10), expect_kernel="ws", max_fraction=0.01)
+
+
+def test_lab_conversion_stage_matches_the_reference():
+    """ColorConversion::ImageFromBGR2Lab (headers/colorconversion.hpp:18-86) on its own: the device Lab image against the
+    oracle's float64 restatement, over all 2^24 BGR triples.  The kernels keep Lab in float32: the bar is the float32
+    rounding of the reference's double (<= 1 float ulp where the device pow differs from glibc's in the last double bit)."""
+    from simplestereo_b200 import _cabi
+    v = np.arange(1 << 24, dtype=np.uint32)
+    img = np.stack([v & 255, (v >> 8) & 255, v >> 16], axis=1).astype(np.uint8).reshape(4096, 4096, 3)
+    gpu = _cabi.lab(img)
+    ref = oracle.bgr2lab(img)
+    exact = gpu == ref.astype(np.float32)
+    err = np.abs(gpu.astype(np.float64) - ref)
+    tol = np.maximum(np.abs(ref), 1.0) * 2.0 ** -22
+    assert (err <= tol).all(), f"max Lab error {err.max():.3e}"
+    assert exact.mean() > 0.9999, f"only {exact.mean():.6f} of the Lab components are the exact float32 rounding"
+    parity.record("lab_all_colours", components=int(exact.size), exact_float32_rounding=int(exact.sum()), max_abs_err=float(err.max()))
 
 
 # ---- API / validation behaviour (SURVEY 3.6) ------------------------------------------------------
@@ -259,6 +335,89 @@ def test_disparity_range_shards_merge_equals_unsharded():
     assert np.array_equal(out.cpu().numpy(), want)
 
 
+def test_disparity_shards_of_a_near_tie_stress_pair_equal_unsharded():
+    """Saturated i.i.d. noise: every argmin is a rounding tie, so any difference in arithmetic between the sharded and
+    the unsharded call would show.  Shards that start inside a 128-disparity chunk run the same kernel on the same
+    chunk grid as the whole call (include/ss_passive.h), hence bit-identical keys."""
+    import torch
+    from simplestereo_b200 import _cabi
+    from simplestereo_b200.sharding import disparity_shards
+    l, r = cases.load_inputs(("noise", (200, 24, 9)))
+    h, w = l.shape[:2]
+    for (mind, maxd, win) in ((0, 100, 15), (3, 200, 9)):
+        want = ss.passive.StereoASW(win, maxd, mind, 5.0, 17.5, True).compute(l, r)
+        assert _cabi.last_kernel()[0] == "tc"
+        L = _cabi.lib()
+        dl, dr = torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()
+        st = torch.cuda.current_stream().cuda_stream
+        for n in (3, 8):
+            keys = torch.empty((n * 2, h * w), dtype=torch.int64, device="cuda")
+            for k, (d0, d1) in enumerate(disparity_shards(mind, maxd, n)):
+                _cabi.check(L.ss_asw_partial_device(dl.data_ptr(), dr.data_ptr(), w, h, win, maxd, mind, 5.0, 17.5, 1, 0, h, d0, d1,
+                                                    keys[2 * k].data_ptr(), keys[2 * k + 1].data_ptr(), st))
+            _cabi.check(L.ss_merge_keys_device(keys.data_ptr(), n, 2 * h * w, st))
+            out = torch.empty((h, w), dtype=torch.int16, device="cuda")
+            _cabi.check(L.ss_finalize_keys_device(keys[0].data_ptr(), keys[1].data_ptr(), w, h, mind, out.data_ptr(), st))
+            torch.cuda.synchronize()
+            assert np.array_equal(out.cpu().numpy(), want), (mind, maxd, n)
+
+
+def test_calls_on_different_streams_do_not_race_on_the_cached_scratch():
+    """The device entry points share the per-device scratch; a call on another stream must wait for the previous one."""
+    import torch
+    from simplestereo_b200 import _cabi
+    L = _cabi.lib()
+    pairs = [synth_pair(400, 60, 100, 50 + k)[:2] for k in range(4)]
+    m = ss.passive.StereoASW(21, 100, 0, 5.0, 17.5, True)
+    want = [m.compute(l, r) for l, r in pairs]
+    dev = [(torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()) for l, r in pairs]
+    outs = [torch.empty((60, 400), dtype=torch.int16, device="cuda") for _ in pairs]
+    streams = [torch.cuda.Stream() for _ in pairs]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for (dl, dr), o, s in zip(dev, outs, streams):
+            _cabi.check(L.ss_asw_compute_device(dl.data_ptr(), dr.data_ptr(), 400, 60, *m._args(), 0, 60, o.data_ptr(), s.cuda_stream))
+        g = ss.passive.StereoGSW(9, 100).compute(*pairs[0])           # a host call on the library's own stream in between
+        torch.cuda.synchronize()
+        for o, w_ in zip(outs, want):
+            assert np.array_equal(o.cpu().numpy(), w_)
+        assert g.shape == (60, 400)
+
+
+def test_devices_kwarg_shards_rows_over_gpus_in_process():
+    """StereoASW(devices=[0, 1]).compute == one GPU, bit for bit (ss_init_devices: one host thread + context per GPU)."""
+    import torch
+    from simplestereo_b200 import _cabi
+    n = torch.cuda.device_count()
+    l, r, _ = synth_pair(500, 90, 100, 61)
+    kw = dict(winSize=21, maxDisparity=100, minDisparity=0, gammaC=5, gammaP=17.5, consistent=True)
+    _cabi.use_devices([0])
+    want = ss.passive.StereoASW(**kw).compute(l, r)
+    wantg = ss.passive.StereoGSW(9, 100).compute(l, r)
+    try:
+        devs = list(range(min(n, 4)))
+        assert np.array_equal(ss.passive.StereoASW(devices=devs, **kw).compute(l, r), want)
+        assert _cabi.lib().ss_device_count() == len(devs)
+        assert np.array_equal(ss.passive.StereoGSW(9, 100, devices=devs).compute(l, r), wantg)
+        assert np.array_equal(ss.passive.StereoASW(devices="all", **kw).compute(l, r, rows=(7, 80)), want[7:80])
+        if n >= 2:
+            # device-resident form: one grouped in-place ncclAllGather leaves the whole map on every device
+            import ctypes
+            devs = list(range(n))
+            _cabi.init_devices(devs)
+            S = -(-90 // n)
+            dl = [torch.from_numpy(l).to(f"cuda:{k}") for k in devs]
+            dr = [torch.from_numpy(r).to(f"cuda:{k}") for k in devs]
+            do = [torch.zeros((n * S, 500), dtype=torch.int16, device=f"cuda:{k}") for k in devs]
+            arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])
+            win, maxd, mind, gc, gp, cons = ss.passive.StereoASW(**kw)._args()
+            _cabi.check(_cabi.lib().ss_asw_compute_multi_device(arr(dl), arr(dr), 500, 90, win, maxd, mind, gc, gp, cons, arr(do), None))
+            for o in do:
+                assert np.array_equal(o.cpu().numpy()[:90], want)
+    finally:
+        _cabi.use_devices([0])
+
+
 def test_row_stripes_device_entry_point():
     import torch
     from simplestereo_b200 import _cabi
@@ -286,12 +445,10 @@ def test_c4_full_size_middlebury_lr_consistency():
     kw = dict(winSize=51, maxDisparity=255, minDisparity=0, gammaC=5, gammaP=17.5, consistent=True)
     m = ss.passive.StereoASW(**kw)
     gpu = m.compute_staged(l, r)
-    rows = (1000, 1002)
-    ref = oracle.asw(l, r, stages=True, cost=True, rows=rows, **kw)
-    sl = slice(*rows)
-    g = {k: gpu[k][sl] for k in ("left", "right", "invalid", "final")}
-    rr = {k: ref[k][sl] for k in ("left", "right", "invalid", "final")}
-    parity.check_staged(g, rr, ref["cost"], ref["cost"], 0, True)
+    for rows in ((1000, 1002), (0, 1), (1987, 1988)):
+        g, ref, nl, nr = _stripe_parity(f"c4_full_rows{rows[0]}", l, r, kw, rows, expect_kernel="ws")
+        for k in ("left", "right", "invalid", "final"):
+            assert np.array_equal(g[k], gpu[k][slice(*rows)])
     for r0, r1 in ((0, 3), (994, 1003), (1985, 1988)):
         assert np.array_equal(m.compute(l, r, rows=(r0, r1)), gpu["final"][r0:r1])
     assert (gpu["left"] == gt).mean() > 0.85
@@ -325,34 +482,25 @@ def test_c5_full_size_4k_disparity_shards_equal_unsharded():
     assert np.array_equal(out.cpu().numpy(), want)
     del keys, out, dl, dr
     torch.cuda.empty_cache()
-    rows = (1080, 1081)
-    ref = oracle.asw(l, r, stages=True, cost=True, rows=rows, **kw)
-    parity.adjudicate_left(want[rows[0]:rows[1]], ref["left"][rows[0]:rows[1]], ref["cost"], 0)
+    for rows in ((1080, 1081), (2159, 2160)):
+        g, ref, nl, nr = _stripe_parity(f"c5_full_rows{rows[0]}", l, r, kw, rows, expect_kernel="tc")
+        assert np.array_equal(g["final"], want[slice(*rows)])
     assert (want == gt).mean() > 0.80
     assert want.min() >= 0 and want.max() <= 511
 
 
-def test_gsw_large_window_falls_back_to_single_role_kernel(monkeypatch):
-    """win 51 at DC 128: the float raw-cost tiles do not fit the double-buffered staging of k_aggregate_ws, the call is
-    served by the single-role k_aggregate (exact expf / IEEE sqrt weights).  Same parity bar; and the two kernels agree
-    with each other on a window both can run."""
+def test_gsw_large_window_runs_narrower_chunks():
+    """win 51: the float raw-cost tiles of a 128-disparity chunk do not fit the double-buffered staging of k_aggregate_ws;
+    the call runs 64-disparity chunks instead (merged through the atomicMin keys).  Same parity bar."""
+    from simplestereo_b200 import _cabi
     l, r, _ = synth_pair(200, 20, 100, 12)
     kw = dict(winSize=51, maxDisparity=100, minDisparity=0, gamma=10, fMax=120, iterations=3, bins=20)
     gpu = ss.passive.StereoGSW(**kw).compute_staged(l, r, cost=True)
+    assert _cabi.last_kernel() == ("ws", 64)
     ref = oracle.gsw(l, r, stages=True, cost=True, **kw)
     parity.check_cost(gpu["cost_left"], ref["cost_left"], "cost_left")
     parity.check_cost(gpu["cost_right"], ref["cost_right"], "cost_right")
     parity.check_staged(gpu, ref, ref["cost_left"], ref["cost_right"], 0, True, max_fraction=0.01, saturation=None)
-    kw["winSize"] = 21
-    ws = ss.passive.StereoGSW(**kw).compute_staged(l, r, cost=True)
-    monkeypatch.setenv("SS_GSW_SINGLE", "1")
-    single = ss.passive.StereoGSW(**kw).compute_staged(l, r, cost=True)
-    monkeypatch.delenv("SS_GSW_SINGLE")
-    fin = np.isfinite(single["cost_left"])
-    assert np.array_equal(fin, np.isfinite(ws["cost_left"]))
-    assert np.allclose(ws["cost_left"][fin], single["cost_left"][fin], rtol=2e-5, atol=1e-5)
-    assert np.allclose(ws["cost_right"][fin], single["cost_right"][fin], rtol=2e-5, atol=1e-5)
-    assert (ws["final"] != single["final"]).mean() < 0.01
 
 
 def test_c_abi_from_plain_c(tmp_path):
@@ -388,13 +536,15 @@ def test_tensor_core_and_cuda_core_aggregation_agree(monkeypatch):
     SS_TCDEN=0 forces the all-CUDA-core k_aggregate_ws.  Same parity bar for both, and they must agree with each other:
     costs to 5e-5, maps except at near-ties."""
     l, r, _ = synth_pair(330, 44, 139, 17)
-    for win in (35, 51):                                   # double-staged and single-staged operand variants
+    from simplestereo_b200 import _cabi
+    for win in (35, 41):                                   # double-staged and single-staged operand variants
         kw = dict(winSize=win, maxDisparity=139, minDisparity=0, gammaC=9.0, gammaP=25.0, consistent=True)
         ref = oracle.asw(l, r, stages=True, cost=True, **kw)
         out = {}
         for tc in ("1", "0"):
             monkeypatch.setenv("SS_TCDEN", tc)
             out[tc] = ss.passive.StereoASW(**kw).compute_staged(l, r, cost=True)
+            assert _cabi.last_kernel()[0] == ("tc" if tc == "1" else "ws")
             parity.check_cost(out[tc]["cost"], ref["cost"])
             parity.check_staged(out[tc], ref, ref["cost"], ref["cost"], 0, True, max_fraction=0.01)
         monkeypatch.delenv("SS_TCDEN")

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from simplestereo_b200.sharding import disparity_shards, gather_rows, row_stripes
+from simplestereo_b200.sharding import chunk_size, disparity_row_grid, disparity_shards, gather_rows, row_stripes
 
 
 def test_row_stripes_cover_all_rows():
@@ -31,6 +31,49 @@ def test_disparity_shards_cover_range():
             sh = disparity_shards(lo, hi, n)
             ds = [d for d0, d1 in sh for d in range(d0, d1 + 1)]
             assert ds == list(range(lo, hi + 1))
+
+
+def test_disparity_row_grid_covers_every_pair_once_on_chunk_boundaries():
+    for (lo, hi) in ((0, 127), (4, 14), (0, 0), (5, 3), (0, 511), (3, 150), (0, 255), (7, 300)):
+        for h in (1, 21, 375):
+            for n in (1, 2, 3, 4, 8):
+                n_d, n_r, parts = disparity_row_grid(lo, hi, h, n)
+                assert n_d * n_r == n and len(parts) == n
+                dc = chunk_size(lo, hi)
+                seen = np.zeros((h, max(hi - lo + 1, 0)), np.int32)
+                for rank, (d0, d1, r0, r1) in enumerate(parts):
+                    assert rank == (rank // n_r) * n_r + rank % n_r
+                    if d1 >= d0:
+                        assert (d0 - lo) % dc == 0                      # shards start on the library's chunk grid
+                        assert d1 == hi or (d1 + 1 - lo) % dc == 0
+                        seen[r0:r1, d0 - lo:d1 - lo + 1] += 1
+                assert (seen == 1).all()
+    # C5: 512 disparities on 8 GPUs -> 4 chunk groups x 2 row halves
+    n_d, n_r, parts = disparity_row_grid(0, 511, 2160, 8)
+    assert (n_d, n_r) == (4, 2) and parts[0] == (0, 127, 0, 1080) and parts[7] == (384, 511, 1080, 2160)
+
+
+def test_disparity_row_grid_key_layout_merges_to_the_unsharded_winners():
+    """The layout ShardedStereoASW(mode="disparity") relies on: all_gather concatenates the ranks' key planes as
+    [kd][kr][plane][S*W]; an element-wise min over kd (ss_merge_keys_device with n = n_r*planes*S*W) leaves the merged
+    planes of stripe kr at slot kr."""
+    rng = np.random.default_rng(3)
+    h, w, lo, hi, world, planes = 11, 17, 0, 299, 8, 2
+    cost = rng.random((planes, h, w, hi - lo + 1)).astype(np.float32)
+    keys_of = lambda c, d: (c.view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.uint64(d)
+    want = np.full((planes, h, w), np.iinfo(np.uint64).max, np.uint64)
+    for d in range(lo, hi + 1):
+        want = np.minimum(want, keys_of(cost[..., d - lo], d))
+    n_d, n_r, parts = disparity_row_grid(lo, hi, h, world)
+    S = -(-h // n_r)
+    allk = np.full((world, planes, S * w), np.iinfo(np.uint64).max, np.uint64)
+    for rank, (d0, d1, r0, r1) in enumerate(parts):
+        for d in range(d0, d1 + 1):
+            k = keys_of(cost[:, r0:r1, :, d - lo], d).reshape(planes, -1)
+            allk[rank, :, :k.shape[1]] = np.minimum(allk[rank, :, :k.shape[1]], k)
+    merged = allk.reshape(n_d, n_r * planes * S * w).min(axis=0).reshape(n_r, planes, S, w)
+    got = np.concatenate([merged[kr] for kr in range(n_r)], axis=1)[:, :h]
+    assert np.array_equal(got, want)
 
 
 def _free_port():
