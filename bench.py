@@ -18,13 +18,19 @@ A "step" is one full disparity map of that pair.
           SURVEY.md 8d), with achieved HBM GB/s against MEASURED_PEAKS.json beside it.
   cpu_baseline  the unmodified reference (oracle/_ref) timed on this box's host cores on a bounded full-width
           crop and extrapolated by exact window-element counts (N=1, rank 0 only).
-  other_configs  device-resident ms of the other BASELINE.json configurations (C2 + L-R, C3 GSW, C4, C5) on one GPU,
-          for context only (N=1; --no-other-configs skips them).
+  other_configs  device-resident ms of the other BASELINE.json configurations on one GPU (C2 + L-R, C3 GSW, C4, C5; N=1),
+          and at N > 1 config C5 (4K, 512 disparities) under BOTH partitions SURVEY.md 8(e) names -- image-row stripes and
+          disparity-range shards -- with the flag that all three maps (unsharded, rows, disparity) are bit-identical.
+          --no-other-configs skips them.
 
 At N > 1 the frame is sharded into N image-row stripes (one rank per GPU) and reassembled with one NCCL
-all-gather (strong scaling: total work fixed).
+all-gather (strong scaling: total work fixed); the e2e leg then runs the class API itself,
+StereoASW(devices=[0..N-1]).compute(left, right), in rank 0's process: ss_init_devices shards the rows over the N GPUs
+with one host thread per GPU (the other ranks wait at the barrier).
 
---impl reference times the reference's own CPU implementation (oracle/_ref, else the C port) on the same config.
+--impl reference times the reference's own CPU implementation (oracle/_ref, else the C port) on the same config: every
+step is a bounded full-width crop (ms_per_step is its MEASURED duration, value the full-frame-equivalent throughput), and once
+per invocation the WHOLE C2 frame is timed (cpu_baseline.full_frame_s) to pin the extrapolation.
 """
 import argparse
 import json
@@ -102,7 +108,7 @@ def cpu_reference_sample(target_s, crop_rows=None):
         kind = "port"
     scale = window_elements(W, H, WIN, MIND, MAXD) / window_elements(W, crop_rows, WIN, MIND, MAXD)
     t_full = dt * scale
-    info = {"kind": kind, "cores": cores, "crop_rows": crop_rows,
+    info = {"kind": kind, "cores": cores, "crop_rows": crop_rows, "sample_s": dt,
             "sample": f"full-width {W}x{crop_rows} crop of the workload pair ({dt:.2f} s measured), extrapolated x{scale:.2f} "
                       f"to {W}x{H} by exact window-element counts"}
     return mpixdisp(t_full), info, t_full
@@ -114,13 +120,27 @@ def window_rows(h):
     return int((np.minimum(y, p) + 1 + np.minimum(h - 1 - y, p)).sum())
 
 
+def cpu_reference_full_frame():
+    """One call of the reference on the WHOLE C2 frame ("C1, C2: time the full image").  Seconds."""
+    import oracle
+    from simplestereo_b200.synth import synth_pair
+    left, right, _ = synth_pair(W, H, MAXD, 0)
+    if oracle.ref_available():
+        _, dt = oracle.ref_asw(left, right, WIN, MAXD, MIND, GC, GP, False, with_time=True, timeout=3600)
+        return dt
+    oracle.build(ref=False)
+    t0 = time.perf_counter()
+    oracle.asw(left, right, WIN, MAXD, MIND, GC, GP, False)
+    return time.perf_counter() - t0
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     total = max(args.steps + args.warmup, 1)
     target = min(30.0, max(2.0, 150.0 / total))
-    vals, times = [], []
+    vals, times, samples = [], [], []
     info = None
     rows = None
     for k in range(args.warmup + args.steps):
@@ -129,13 +149,23 @@ def run_reference(args):
         if k >= args.warmup:
             vals.append(v)
             times.append(t_full)
+            samples.append(info["sample_s"])
     value = statistics.median(vals)
+    t_equiv = statistics.median(times)
+    full = None
+    if not args.no_full_frame:
+        full_s = cpu_reference_full_frame()
+        full = {"full_frame_s": full_s, "full_frame_value": mpixdisp(full_s),
+                "extrapolation_error": (t_equiv - full_s) / full_s}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": statistics.median(times) * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": statistics.median(samples) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "ms_per_step is the full-frame time extrapolated from the bounded sample"},
-        "cpu_baseline": {"value": value, "unit": UNIT, **info},
+        "config": {"workload": WORKLOAD,
+                   "note": "a step is one bounded sample (full-width crop) and ms_per_step its measured duration; value is the "
+                           "full-frame-equivalent throughput (exact window-element counts), pinned by cpu_baseline.full_frame_s",
+                   "full_frame_ms_equivalent": t_equiv * 1e3},
+        "cpu_baseline": {"value": value, "unit": UNIT, **info, **(full or {})},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -242,6 +272,64 @@ class ClockSampler:
                 "samples": len(sm), "source": self.source}
 
 
+def c5_partitions(ss, _cabi, L, dev, stream, world, rank, barrier):
+    """BASELINE.json config 5 (3840x2160, 512 disparities, win 35) over `world` GPUs: image-row stripes and disparity-range
+    shards (chunk-aligned groups x row stripes when ranks outnumber the four 128-disparity chunks), device-timed, max over
+    ranks; plus the unsharded call on rank 0 and whether the three maps are bit-identical."""
+    import torch
+    import torch.distributed as dist
+    from simplestereo_b200.sharding import ShardedStereoASW, disparity_row_grid
+    from simplestereo_b200.synth import synth_pair
+    w, h, win, maxd = 3840, 2160, 35, 511
+    l2, r2, _ = synth_pair(w, h, maxd, 0)
+    a, b = torch.from_numpy(l2).to(dev), torch.from_numpy(r2).to(dev)
+    m = ss.passive.StereoASW(win, maxd, 0, GC, GP, consistent=False)
+    out = {}
+    maps = {}
+    for mode in ("rows", "disparity"):
+        sh = ShardedStereoASW(m, mode=mode)
+        maps[mode] = sh.compute_device(a, b).clone()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sh.compute_device(a, b)
+        sh.compute_device(a, b)
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / 2], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[mode] = {"ms": round(float(t.item()), 3), "Mpix_disp_per_s": round(w * h * (maxd + 1) / float(t.item()) / 1e3, 1)}
+        del sh
+    n_d, n_r, _ = disparity_row_grid(0, maxd, h, world)
+    out["disparity"]["grid"] = f"{n_d} disparity groups (chunk-aligned) x {n_r} row stripes"
+    same = torch.tensor([1 if torch.equal(maps["rows"], maps["disparity"]) else 0], device=dev)
+    if rank == 0:
+        full = torch.empty((h, w), dtype=torch.int16, device=dev)
+
+        def run():
+            _cabi.check(L.ss_asw_compute_device(a.data_ptr(), b.data_ptr(), w, h, win, maxd, 0, GC, GP, 0, 0, h, full.data_ptr(),
+                                                stream.cuda_stream))
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        out["one_gpu"] = {"ms": round(e0.elapsed_time(e1), 3)}
+        same *= 1 if torch.equal(full, maps["rows"]) else 0
+        del full
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    barrier()
+    out["maps_bit_identical"] = bool(int(same.item()))
+    if "one_gpu" in out:
+        for mode in ("rows", "disparity"):
+            out[mode]["speedup_vs_one_gpu"] = round(out["one_gpu"]["ms"] / out[mode]["ms"], 2)
+    del a, b, maps
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -327,30 +415,34 @@ def run_b200(args):
     ms_per_step = total_ms / args.steps
     value = mpixdisp(ms_per_step * 1e-3)
 
-    # ---- end-to-end leg: public API, pinned host buffers in, host map out ---------------------------
+    # ---- end-to-end leg: the class API a user calls, pinned host buffers in, host map out -----------------
+    # N = 1: StereoASW.compute on this rank's GPU.  N > 1: rank 0 alone runs StereoASW(devices=[0..N-1]).compute, which
+    # shards the image rows over the N GPUs inside its process (ss_init_devices: one host thread and context per GPU, H2D of
+    # each stripe's rows, kernels, D2H of each stripe into the caller's array); the other ranks wait at the barrier.
     np_left, np_right = h_left.numpy(), h_right.numpy()
-
-    def step_e2e():
+    e2e_matcher = matcher if world == 1 else ss.passive.StereoASW(WIN, MAXD, MIND, GC, GP, consistent=False, devices=list(range(world)))
+    out_host = None
+    barrier()
+    if rank == 0:
+        for _ in range(2):
+            e2e_matcher.compute(np_left, np_right)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out_host = e2e_matcher.compute(np_left, np_right)
+        e2e_s = (time.perf_counter() - t0) / args.steps
         if world > 1:
-            dl = h_left.to(dev, non_blocking=True)
-            dr = h_right.to(dev, non_blocking=True)
-            return sharded.compute_device(dl, dr).cpu()
-        return matcher.compute(np_left, np_right)
-
-    for _ in range(2):
-        step_e2e()
+            _cabi.use_devices([local])
+    else:
+        e2e_s = 0.0
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out_host = step_e2e()
-    barrier()
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
 
     # sanity: device leg and e2e leg produce the same map
-    same = bool(np.array_equal(np.asarray(out_host), result.cpu().numpy()[:H]))
+    same = bool(np.array_equal(np.asarray(out_host), result.cpu().numpy()[:H])) if rank == 0 else None
+
+    # ---- config C5 (4K, 512 disparities) under both multi-GPU partitions (N > 1; every rank takes part) --------------
+    c5 = None
+    if world > 1 and not args.no_other_configs:
+        c5 = c5_partitions(ss, _cabi, L, dev, stream, world, rank, barrier)
 
     if rank != 0:
         if world > 1:
@@ -372,19 +464,28 @@ def run_b200(args):
     agg_avg_s = (agg_ms / max(agg_launches, 1)) * 1e-3
     achieved_tf = flops_per_launch / agg_avg_s / 1e12
     traffic = None
+    traffic_note = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         traffic = prof.get("k_aggregate_dram_bytes_per_launch")
+        traffic_note = prof.get("source")
+        if traffic is not None and world > 1:
+            # the capture is of the one-GPU launch (all 375 rows); a rank's launch covers rows_per_rank rows plus the halo
+            traffic = traffic * (rows_per_rank + WIN - 1) / (H + WIN - 1)
+            traffic_note = f"{traffic_note}; scaled to this rank's {rows_per_rank} rows (+{WIN - 1} halo rows)"
     except Exception:
         pass
+    pipe_flops = 3.0 * W * rows_per_rank * D * WIN * WIN               # mul + fma: what the CUDA cores execute per element
     roofline = {
         "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
-        "traffic": traffic,
-        "kernel": "k_aggregate_tc<ASW, DC=128> (warp-specialised support-weight aggregation + WTA; numerators on packed FP32, denominators on tcgen05 3xTF32)", "kernel_ms": agg_avg_s * 1e3, "kernel_share_of_step": agg_ms / total_ms if world == 1 else None,
+        "traffic": traffic, "traffic_source": traffic_note,
+        "kernel": "k_aggregate_tc<ASW, DC=128> (warp-specialised support-weight aggregation + WTA for both references; numerators on packed FP32, denominators on tcgen05 3xTF32)", "kernel_ms": agg_avg_s * 1e3, "kernel_share_of_step": agg_ms / total_ms if world == 1 else None,
         "peak_source": "FFMA-only microbenchmark run live on this GPU (ss_measure_fp32_peak); nominal 74.4 TFLOP/s",
         "algorithmic_flops_per_launch": flops_per_launch,
-        "note": "4 algorithmic flop per window element (mul, fma, add); the add (denominator) runs on the tensor cores "
-                "(tcgen05 kind::tf32, 3xTF32) and is not counted twice; ncu: tensor pipe 11 % active, see profiles/",
+        "note": "frac counts the 4 ALGORITHMIC flop per window element (mul, fma, add; SURVEY.md 8d) against the FFMA peak; "
+                "the add (denominator) runs on the tensor cores (tcgen05 kind::tf32, 3xTF32), so the FP32 pipe itself executes "
+                "3 flop per element: fp32_pipe is that utilisation",
+        "fp32_pipe": {"flops_per_element": 3, "achieved": pipe_flops / agg_avg_s / 1e12, "frac": pipe_flops / agg_avg_s / 1e12 / fp32_peak},
         "hbm": {"achieved": bytes_per_launch / agg_avg_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": bytes_per_launch / agg_avg_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch},
@@ -425,6 +526,8 @@ def run_b200(args):
             except Exception as ex:
                 others[name] = {"error": repr(ex)[:120]}
         torch.cuda.empty_cache()
+    if c5 is not None:
+        others = {"C5 3840x2160 D512 win35 sharded over %d GPUs" % world: c5}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -439,6 +542,7 @@ def run_b200(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sharding": "none" if world == 1 else f"{world} image-row stripes + one NCCL all_gather",
+                   "e2e_path": "StereoASW.compute (one GPU)" if world == 1 else f"StereoASW(devices=[0..{world - 1}]).compute in one process: rows sharded over {world} GPUs, one host thread each, no collective",
                    "l2": "flushed between timed steps (256 MiB fill)", "timing": "CUDA events per step on the launching stream, max over ranks",
                    "maps_equal_across_legs": same},
         "clocks": clocks,
@@ -464,6 +568,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-full-frame", action="store_true", help="reference arm: skip the one full-frame call (~45 s on 16 cores)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -49,8 +49,8 @@ int ss_init(int device);
  * `devices[0..n)` -- one host thread and one context (stream, cached scratch) per device, every device reading the rows it
  * needs from the caller's arrays and writing its stripe straight into the caller's output, no collective -- exactly the
  * unit the reference's workers pop from their queue (a row index, _passive.cpp:372-374).  devices == NULL or n <= 0 selects
- * every visible device.  When n > 1 the NCCL communicators of ss_*_compute_multi_device are created too
- * (ncclCommInitAll; libnccl.so.2 is loaded at run time and its absence is not an error here).
+ * every visible device.  (The NCCL communicators of ss_*_compute_multi_device are created by its first call:
+ * ncclCommInitAll over this list, libnccl.so.2 loaded at run time.)
  * The device-resident entry points always run on the caller's CURRENT device, whatever this list holds. */
 int ss_init_devices(const int *devices, int n);
 /* number of devices in the list (0 before ss_init / ss_init_devices) */

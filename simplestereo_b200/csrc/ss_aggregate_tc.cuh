@@ -31,8 +31,8 @@
 //     SINGLE (39 < win <= 79): one stage of A, 192 + 2 KC half + KC (hi|lo) + j with KC = 8 ceil(win / 8), and one stage of
 //     the left-weight residual in shared memory; the producers then wait for the previous row's MMAs (a second commit onto
 //     barrier 7) before they overwrite them -- a stall of one MMA batch per window row instead of a second buffer.
-//   * one thread (producer 3, lane 0) issues the 30 tcgen05.mma per window row and commits them onto the "weight stage
-//     free" mbarrier, whose count is consumers + 1.
+//   * one thread (the utility warp: lane 0 of warp 16, which also drives the TMA copies) issues the 30 tcgen05.mma per
+//     window row and commits them onto the "weight stage free" mbarrier, whose count is consumers + 1.
 
 constexpr int TC_SBO = 144;                       // bytes between 8-column groups of the left-weight operand
 constexpr int TC_LBO = (TILE_WS / 8) * TC_SBO;    // bytes between the two 4-offset chunks of a K group
@@ -82,9 +82,11 @@ __device__ __forceinline__ void tc_st4(uint32_t taddr, uint32_t a, uint32_t b, u
 }
 __device__ __forceinline__ float tc_lo(float w) { return __fsub_rn(w, __uint_as_float(__float_as_uint(w) & 0xffffe000u)); }
 
+constexpr int TC_THREADS = 544;                   // 12 consumer + 4 producer + 1 utility warp
+
 template <int REM, bool SINGLE>
-__global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
-    constexpr int DC = 128, T = TILE_WS, NRp = T + DC, EP = DC + 4, CW = 12, PW = 4, NDB = 4, NT = 512;
+__global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams P) {
+    constexpr int DC = 128, T = TILE_WS, NRp = T + DC, EP = DC + 4, CW = 12, PW = 4, NDB = 4, NT = TC_THREADS;
     extern __shared__ __align__(128) unsigned char smem[];
 
     const Geom &g = P.g;
@@ -100,16 +102,18 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 128);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * T;
-    const int y = g.row0 + blockIdx.y;
-    const int ch = blockIdx.z;
+    const int tile = g.tile0 + (int)blockIdx.x, per_ch = g.ntx * (g.row1 - g.row0);
+    const int ch = tile / per_ch, rem = tile - ch * per_ch;
+    const int x0 = (rem % g.ntx) * T;
+    const int y = g.row0 + rem / g.ntx;
+    const int xsub = g.nsub > 1 ? (int)blockIdx.y : -1;     // tail launch: only this 32-column block of the tile (ss_passive.cu)
     const int dlo = g.dLo + ch * DC;
     const int erows = g.erow1 - g.erow0;
     const int i_lo = max(0, pad - y), i_hi = min(win - 1, g.H - 1 - y + pad);
     const int nsteps = i_hi - i_lo + 1;
 
     if (x0 + T - 1 < dlo) {                        // no evaluated pair in this tile (see k_aggregate_ws)
-        if (P.vol_export) {
+        if (P.vol_export && xsub <= 0) {
             const int rowo = y - g.row0;
             for (int k = tid; k < T * (DC / 4); k += NT) {
                 const int x = x0 + k / (DC / 4), kq = (k % (DC / 4)) * 4;
@@ -148,17 +152,17 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
                       : 192u + (uint32_t)stage * 160u + (uint32_t)half * 80u + (uint32_t)lo * 40u;
     };
 
-    if (warp >= CW) {
-        // =================================== producers ===================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-        const int pw = warp - CW;
-        const uint32_t lane_base = (uint32_t)(pw * 32) << 16;       // this warp's quarter of the TMEM lanes
+    if (warp == CW + PW) {
+        // =================================== utility warp ===================================
+        // One lane drives every asynchronous engine of the block: the TMA bulk copies (features, proximity exponents, raw
+        // costs) and the tcgen05.mma batches.  It used to be a producer lane; measured on the B200 (SS_FREERUN=8): the issue
+        // of a row's 30 MMAs holds the issuing warp for about as long as they run (1.5 k cycles per window row), which
+        // delayed that producer's weights -- and with them the whole block -- by 11 %.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        if (lane != 0) return;
         const int f2_start = x0 - dlo - DC + 1 - pad + g.PL2;
         const int c2_start = x0 - dlo - DC + 1 + g.PL2;
         const size_t e_plane = (size_t)g.UW * EP;
-        const float4 *C1s = reinterpret_cast<const float4 *>(smem + sp.c1);
-        const float4 *C2s = reinterpret_cast<const float4 *>(smem + sp.c2);
-
         auto issue_F = [&](int n) {
             const int i = i_lo + n, ii = y - pad + i, st = n & 1;
             const uint32_t bar = BAR(1 + st);
@@ -175,12 +179,57 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
                         static_cast<const uint8_t *>(P.E) + ((size_t)ch * erows + (ii - g.erow0)) * e_plane + (size_t)x0 * EP,
                         (uint32_t)sp.ebytes, bar);
         };
-        if (pw == 0 && lane == 0) {
-            mbar_expect_tx(BAR(0), (uint32_t)((T + NR) * 16));
-            tma_load_1d(smem_u32(smem + sp.c1), P.F1 + (size_t)(y - g.erow0) * g.UW + x0 + pad, T * 16, BAR(0));
-            tma_load_1d(smem_u32(smem + sp.c2), P.F2 + (size_t)(y - g.erow0) * g.VW + c2_start, NR * 16, BAR(0));
-            issue_F(0);
+        mbar_expect_tx(BAR(0), (uint32_t)((T + NR) * 16));
+        tma_load_1d(smem_u32(smem + sp.c1), P.F1 + (size_t)(y - g.erow0) * g.UW + x0 + pad, T * 16, BAR(0));
+        tma_load_1d(smem_u32(smem + sp.c2), P.F2 + (size_t)(y - g.erow0) * g.VW + c2_start, NR * 16, BAR(0));
+        issue_F(0);
+        const uint32_t idesc = tc_idesc(128, T);
+        const int KGx = (P.freerun & 8) ? 0 : KG;         // timing experiment: no MMAs (the commits still arrive)
+        int sw = 0, phw = 0;
+        for (int n = 0; n < nsteps; ++n) {
+            const int st = n & 1, ph = (n >> 1) & 1;
+            if (n + 1 < nsteps) {
+                mbar_wait(BAR(3 + ((n + 1) & 1)), (((n + 1) >> 1) & 1) ^ 1);   // feature stage free
+                issue_F(n + 1);
+            }
+            mbar_wait(BAR(13 + st), ph ^ 1);                                   // raw-cost stage free
+            issue_E(n);
+            // ---- the tensor core: D[r][x] += W2hi*W1hi + W2hi*W1lo + W2lo*W1hi over this window row ----
+            mbar_wait(BAR(5 + sw), phw);                 // every producer has arrived: the operands of this row are in place
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t bhi = smem_u32(smem + sp.w1 + sw * sp.w1arr);
+            const uint32_t blo = smem_u32(smem + sp.w1 + (2 + (SINGLE ? 0 : sw)) * sp.w1arr);
+            for (int half = 0; half < 2; ++half)
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t a0 = tbase + colA(sw, half, term == 2);
+                    const uint32_t b0 = term == 1 ? blo : bhi;
+                    for (int kg = 0; kg < KGx; ++kg) {
+                        const u64 bd = tc_sdesc(b0 + (uint32_t)kg * TC_KGB, TC_LBO, TC_SBO);
+                        const uint32_t acc = !(n == 0 && term == 0 && kg == 0);
+                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tbase + 96u * half),
+                                     "r"(a0 + 8u * kg), "l"(bd), "r"(idesc), "r"(acc)
+                                     : "memory");
+                    }
+                }
+            // completion of everything issued so far arrives on "weight stage free" (and on barrier 7 when the operands are
+            // single-staged)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(8 + sw)) : "memory");
+            if (SINGLE)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(7)) : "memory");
+            if (++sw == 2) { sw = 0; phw ^= 1; }
         }
+        return;
+    }
+
+    if (warp >= CW) {
+        // =================================== producers ===================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        const int pw = warp - CW;
+        const uint32_t lane_base = (uint32_t)(pw * 32) << 16;       // this warp's quarter of the TMEM lanes
+        const float4 *C1s = reinterpret_cast<const float4 *>(smem + sp.c1);
+        const float4 *C2s = reinterpret_cast<const float4 *>(smem + sp.c2);
+
         // K padding: window offsets in [win, 8 KG) must contribute 0.  Zero every A column of this warp's TMEM lanes and
         // the whole left-weight operand once; offsets inside the last written batch are zeroed when they are written.
         for (int c = 0; c < (SINGLE ? (int)(4u * KC) : 320); c += 4) tc_st4(tbase + lane_base + 192u + c, 0u, 0u, 0u, 0u);
@@ -191,24 +240,21 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
 
         const int NB = winq;                                        // batches of 4 window offsets per column block
         // left-weight batches (3 column blocks x NB) are split so that every producer tabulates the same number of batches:
-        // producers 0-2 own two right-column blocks (cb = pw, pw + 4), producer 3 only one -- and it issues the MMAs.
-        const int l0 = pw == 0 ? 0 : pw == 1 ? (NB * 5) / 9 : pw == 2 ? (NB * 11) / 9 : (NB * 16) / 9;
-        const int l1 = pw == 0 ? (NB * 5) / 9 : pw == 1 ? (NB * 11) / 9 : pw == 2 ? (NB * 16) / 9 : 3 * NB;
+        // producers 0-2 own two right-column blocks (cb = pw, pw + 4), producer 3 only one.
+        // A block restricted to x-block xsub needs right centres r = T-1-x+k with x in the block (column blocks cbr0..cbr1)
+        // and one left block; everything else stays at the zeros written below.
+        const int cbr0 = xsub < 0 ? 0 : T / 32 - 1 - xsub, cbr1 = xsub < 0 ? NRp / 32 - 1 : (T - 1 - 32 * xsub + DC - 1) / 32;
+        const int l0 = xsub >= 0 ? xsub * NB + (pw * NB) / 4
+                                 : pw == 0 ? 0 : pw == 1 ? (NB * 5) / 9 : pw == 2 ? (NB * 11) / 9 : (NB * 16) / 9;
+        const int l1 = xsub >= 0 ? xsub * NB + ((pw + 1) * NB) / 4
+                                 : pw == 0 ? (NB * 5) / 9 : pw == 1 ? (NB * 11) / 9 : pw == 2 ? (NB * 16) / 9 : 3 * NB;
+        const int l0_blk = l0 / NB, l0_jb = l0 - l0_blk * NB;
         const int o_f1 = sp.f1, o_f2 = sp.f2, o_pa = sp.pa, o_w1 = sp.w1, o_w2 = sp.w2;
         const int b_f1 = sp.f1bytes, b_f2 = sp.f2bytes, b_pa = sp.pabytes, b_w2 = sp.w2bytes, w1arr = sp.w1arr;
 
         int sw = 0, phw = 0;
         for (int n = 0; n < nsteps; ++n) {
             const int st = n & 1, ph = (n >> 1) & 1;
-            if (pw == 0 && lane == 0) {
-                if (n + 1 < nsteps) {
-                    mbar_wait(BAR(3 + ((n + 1) & 1)), (((n + 1) >> 1) & 1) ^ 1);
-                    issue_F(n + 1);
-                }
-                mbar_wait(BAR(13 + st), ph ^ 1);
-                issue_E(n);
-            }
-            __syncwarp();
             if (n == 0) mbar_wait(BAR(0), 0);
             mbar_wait(BAR(1 + st), ph);            // features of this window row have landed
             mbar_wait(BAR(8 + sw), phw ^ 1);  // consumers AND the tensor core are done with this weight stage
@@ -224,7 +270,8 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
 
             // ---- right columns: consumer copy (row-major, reversed index) + tensor-memory copy (hi, lo) ----
 #pragma unroll 1
-            for (int cb = pw; cb < NRp / 32; cb += 4) {
+            for (int cb = pw; cb < ((P.freerun & 2) ? 0 : NRp / 32); cb += 4) {
+                if (cb < cbr0 || cb > cbr1) continue;
                 const int col = cb * 32 + lane;                      // r; column NR is padding (never read)
                 const int src = NR - 1 - col;
                 const float4 c = C2s[src];
@@ -253,9 +300,9 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
                 }
             }
             // ---- left columns: K-major operand shared by the consumers and the tensor core (hi) + its residual (lo) ----
-#pragma unroll 1
-            for (int lb = l0; lb < l1; ++lb) {
-                const int blk = lb / NB, jb = lb - blk * NB;
+            int blk = l0_blk, jb = l0_jb;                            // (column block, batch) of lb, kept without a division
+#pragma unroll 2
+            for (int lb = l0; lb < ((P.freerun & 2) ? l0 : l1); ++lb) {
                 const int col = blk * 32 + lane;                     // x
                 const float4 c = C1s[col];
                 const float4 *nb = f1 + col + 4 * jb;
@@ -273,6 +320,7 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
                 const int qo = (jb >> 1) * TC_KGB + (jb & 1) * TC_LBO + (col >> 3) * TC_SBO + (col & 7) * 16;
                 *reinterpret_cast<float4 *>(W1hi + qo) = make_float4(w0, w1, w2, w3);
                 *reinterpret_cast<float4 *>(W1lo + qo) = make_float4(tc_lo(w0), tc_lo(w1), tc_lo(w2), tc_lo(w3));
+                if (++jb == NB) { jb = 0; ++blk; }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -281,34 +329,6 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
             if (lane == 0) {
                 mbar_arrive(BAR(5 + sw));        // weights ready
                 mbar_arrive(BAR(3 + st));        // feature stage may be refilled
-            }
-            if (pw == 3) {
-                // ---- the tensor core: D[r][x] += W2hi*W1hi + W2hi*W1lo + W2lo*W1hi over this window row ----
-                mbar_wait(BAR(5 + sw), phw);     // every producer has arrived
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const uint32_t idesc = tc_idesc(128, T);
-                    const uint32_t bhi = smem_u32(W1hi), blo = smem_u32(W1lo);
-                    for (int half = 0; half < 2; ++half)
-                        for (int term = 0; term < 3; ++term) {
-                            const uint32_t a0 = tbase + colA(sw, half, term == 2);
-                            const uint32_t b0 = term == 1 ? blo : bhi;
-                            for (int kg = 0; kg < KG; ++kg) {
-                                const u64 bd = tc_sdesc(b0 + (uint32_t)kg * TC_KGB, TC_LBO, TC_SBO);
-                                const uint32_t acc = !(n == 0 && term == 0 && kg == 0);
-                                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tbase + 96u * half),
-                                             "r"(a0 + 8u * kg), "l"(bd), "r"(idesc), "r"(acc)
-                                             : "memory");
-                            }
-                        }
-                    // completion of everything issued so far arrives on "weight stage free" (and on barrier 7 when the
-                    // operands are single-staged)
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(8 + sw)) : "memory");
-                    if (SINGLE)
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(7)) : "memory");
-                }
-                __syncwarp();
             }
             if (++sw == 2) { sw = 0; phw ^= 1; }
         }
@@ -349,7 +369,8 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
     const int xg = (warp / NDB) * 4 + xl;
     const int dg = ((warp % NDB) * 8 + dl + 2 * xl) % (DC / 4);
     const int xb = 8 * xg, kb = 4 * dg;
-    const bool lane_live = (x0 + xb < g.W) && (dlo + kb <= g.dHi) && (dlo + kb + 3 >= g.dVLo) && (x0 + xb + 7 >= dlo + kb);
+    const bool sub_ok = xsub < 0 || warp / NDB == xsub;     // warp-uniform
+    const bool lane_live = sub_ok && (x0 + xb < g.W) && (dlo + kb <= g.dHi) && (dlo + kb + 3 >= g.dVLo) && (x0 + xb + 7 >= dlo + kb);
     const bool warp_live = __any_sync(0xffffffffu, lane_live);
     const int R0 = T - 8 - xb + kb;
 
@@ -362,7 +383,7 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
         const int st = n & 1, ph = (n >> 1) & 1;
         mbar_wait(BAR(5 + sw), phw);             // weights of this window row
         mbar_wait(BAR(11 + st), ph);             // raw costs of this window row
-        if (warp_live) {
+        if (warp_live && !(P.freerun & 4)) {
             u64 ring[8][2];
             const uint8_t *ep = smem + (sp.e + st * sp.ebytes) + xb * EP + kb;
             auto load_e = [&](const uint8_t *q, u64 &lo, u64 &hi) {
@@ -448,7 +469,7 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int d = dlo + kb + b;
-            const bool valid = (x < g.W) && (d >= g.dVLo) && (d <= g.dHi) && (x - d >= 0);
+            const bool valid = sub_ok && (x < g.W) && (d >= g.dVLo) && (d <= g.dHi) && (x - d >= 0);
             float *dp = Ds + (T - 1 - (xb + a) + kb + b) * T + xb + a;
             // valid window columns of this pair: right column x-d-pad+j >= 0 and left column x-pad+j < W (_passive.cpp:67-68)
             const int jlo = max(0, pad - (x - d)), jhi = min(win - 1, g.W - 1 - x + pad);
@@ -467,7 +488,7 @@ __global__ void __launch_bounds__(512, 1) k_aggregate_tc(const AggParams P) {
             best = o < best ? o : best;
         }
         if ((lane & 7) == 0 && x < g.W && best != KEY_NONE) atomicMin(P.bestL + (size_t)rowo * g.W + x, best);
-        if (x < g.W && P.vol0) {
+        if (x < g.W && P.vol0 && sub_ok) {
             const size_t o = ((size_t)rowo * g.W + x) * P.Dp + (size_t)ch * DC + kb;
             *reinterpret_cast<float4 *>(P.vol0 + o) = make_float4(out0[0], out0[1], out0[2], out0[3]);
         }

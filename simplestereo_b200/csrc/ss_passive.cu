@@ -159,7 +159,10 @@ struct Geom {
     int DC, nch;       // disparity chunk, number of chunks covering [dLo, dHi]
     int row0, row1;    // output rows [row0,row1)
     int erow0, erow1;  // input rows needed [erow0,erow1) = output rows +- pad, clipped
-    int T;             // output columns per block: 64 (k_aggregate, GSW) or 96 (k_aggregate_ws, ASW)
+    int tile0;         // first linear (chunk, row, x tile) index of this launch (blockIdx.x counts from here)
+    int nsub;          // 1, or T/32 for the launch that covers the last partial wave: blockIdx.y then restricts a block
+                       // to ONE 32-column block of its tile (same arithmetic per pair, a third of the work per SM)
+    int T;             // output columns per block: 64 (GSW) or 96 (ASW)
     int EP;            // ASW: bytes per cost-volume column (DC + 4: the +4 skews columns 8 apart onto different banks)
     int ntx;           // number of T-column tiles
     int UW;            // padded row pitch of the left feature image and of the cost volume (u' = u + pad)
@@ -281,7 +284,7 @@ struct AggParams {
     float *vol1;          // optional (debug export only): GSW left cost
     int Dp;               // pitch of vol0/vol1 (= nch*DC)
     int vol_export;       // the volumes are returned to the caller (debug export): unevaluated pairs must read +inf
-    int freerun;          // timing experiment (SS_FREERUN=1): consumers ignore the barriers, producers idle; results are garbage
+    int freerun;          // timing experiments (SS_FREERUN bit mask, see run_device); results are garbage
 #ifdef SS_DEBUG_DUMP
     float *dbg;           // [0]=bx [1]=by [2]=step ; dump of W1s, W2s, Es of that block/step follows at dbg+16
 #endif
@@ -358,12 +361,15 @@ template <bool GSW, int DC> struct WsCfg {
     // by two producer warps per scheduler or the consumers wait for them (ncu: 45 % of consumer samples)
     static constexpr int PW = GSW ? SS_GSW_PW * NDB : NDB;
     static constexpr int NT = (CW + PW) * 32;    // ASW 512 / 256 / 128 threads, GSW 512 / 256 / 128
-    static constexpr int MINB = GSW ? 1 : 4 / NDB;   // blocks per SM the register budget is sized for
+    // blocks per SM the register budget is sized for.  DC = 32 (128 threads): 3 blocks -> 168 registers, no spills (4 blocks
+    // = 128 registers spilled 72-120 bytes in the hot loop)
+    static constexpr int MINB = GSW ? 1 : (NDB == 1 ? 3 : 4 / NDB);
     static constexpr int NRp = T + DC;
     static constexpr int EP = GSW ? DC * 4 : DC + 4;   // bytes per raw-cost column (ASW: bytes, skewed by 4)
-    // ASW blocks hold 3 consumer warps per producer warp at every DC (several blocks per SM below 128): the producers give
-    // registers to the consumers (56 / 152 of the 128 the launch allots), which removes the spills of a flat 128 budget
-    static constexpr bool SETREG = !GSW;
+    // 16 warps: the producers give registers to the consumers.  setmaxnreg must be executed by whole warpgroups (4 aligned
+    // warps) with the same operand: only the DC = 128 block (12 consumer + 4 producer warps) is laid out that way -- a
+    // 3 + 1 warp block (DC = 32) that tried it deadlocked on the B200.
+    static constexpr bool SETREG = !GSW && DC == 128 && NT == 512;
 };
 
 struct WsSmem {         // stage s of a double-buffered region lives at base + s * size
@@ -430,9 +436,11 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
     auto BAR = [&](int slot) { return bar0 + 8u * (uint32_t)slot; };
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * T;
-    const int y = g.row0 + blockIdx.y;
-    const int ch = blockIdx.z;
+    const int tile = g.tile0 + (int)blockIdx.x, per_ch = g.ntx * (g.row1 - g.row0);
+    const int ch = tile / per_ch, rem = tile - ch * per_ch;
+    const int x0 = (rem % g.ntx) * T;
+    const int y = g.row0 + rem / g.ntx;
+    const int xsub = g.nsub > 1 ? (int)blockIdx.y : -1;     // tail launch: only this 32-column block of the tile
     const int dlo = g.dLo + ch * DC;
     const int erows = g.erow1 - g.erow0;
     const int i_lo = max(0, pad - y), i_hi = min(win - 1, g.H - 1 - y + pad);
@@ -441,7 +449,7 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
     // Tiles left of the chunk's first disparity hold no evaluated pair (x - d < 0 everywhere): at D = 512 that is 4 %
     // of the blocks.  Their winner keys stay KEY_NONE; the volumes are only touched when they are exported.
     if (x0 + T - 1 < dlo) {
-        if (P.vol_export) {
+        if (P.vol_export && xsub <= 0) {
             const int rowo = y - g.row0;
             for (int k = tid; k < T * (DC / 4); k += C::NT) {
                 const int x = x0 + k / (DC / 4), kq = (k % (DC / 4)) * 4;
@@ -506,7 +514,12 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
             tma_load_1d(smem_u32(smem + sp.c2), P.F2 + (size_t)(y - g.erow0) * g.VW + c2_start, NR * 16, BAR(0));
             issue_F(0);
         }
-        constexpr int NCBR = NRp / 32, NCB = NCBR + T / 32;   // 32-column blocks: right image first, then left
+        constexpr int NCBR = NRp / 32;                       // 32-column blocks: right image first, then left
+        // a block restricted to x-block xsub needs right centres r = T-1-x+k, x in the block: blocks cbr0 .. cbr0+nbr-1, and
+        // one left block
+        const int cbr0 = xsub < 0 ? 0 : T / 32 - 1 - xsub;
+        const int nbr = xsub < 0 ? NCBR : (T - 1 - 32 * xsub + DC - 1) / 32 - cbr0 + 1;
+        const int NCB = nbr + (xsub < 0 ? T / 32 : 1);
         const int NB = winq;                                 // batches of 4 window offsets
         const int npairs = NCB * NB;                         // (column block, batch) pairs, split evenly over the producers
         const int p_begin = (pw * npairs) / PW, p_end = ((pw + 1) * npairs) / PW;
@@ -540,8 +553,8 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
 #pragma unroll 1
             while (left_pairs > 0) {
                 // ---- per column block: centre, neighbour row, destination column ----
-                const bool right = cb < NCBR;                 // warp-uniform
-                const int col = (right ? cb : cb - NCBR) * 32 + lane;
+                const bool right = cb < nbr;                  // warp-uniform
+                const int col = (right ? cbr0 + cb : (xsub < 0 ? cb - nbr : xsub)) * 32 + lane;
                 // right: W2s[j][r], r reversed (xr = xr_max - r): centre NR-1-r, neighbour NR-1-r+j
                 //        (column r = NR is padding: it reads the float4 in front of C2s and is never used)
                 // left : W1s[j][x], centre (y, x0+x), neighbour (ii, x0+x-pad+j)
@@ -623,7 +636,8 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
     const int kb = 4 * dg;                                   // chunk-relative first disparity
     // A warp none of whose lane tiles holds an evaluated pair (x - d < 0 everywhere, at the left image border, or d
     // beyond the requested range) only keeps the barriers moving.
-    const bool lane_live = (x0 + xb < g.W) && (dlo + kb <= g.dHi) && (dlo + kb + 3 >= g.dVLo) && (x0 + xb + 7 >= dlo + kb);
+    const bool sub_ok = xsub < 0 || warp / C::NDB == xsub;   // warp-uniform
+    const bool lane_live = sub_ok && (x0 + xb < g.W) && (dlo + kb <= g.dHi) && (dlo + kb + 3 >= g.dVLo) && (x0 + xb + 7 >= dlo + kb);
     const bool warp_live = __any_sync(0xffffffffu, lane_live);
     const int R0 = T - 8 - xb + kb;                          // first reversed right-centre index (multiple of 4)
 
@@ -752,7 +766,7 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int d = dlo + kb + b;
-            const bool valid = (x < g.W) && (d >= g.dVLo) && (d <= g.dHi) && (x - d >= 0);
+            const bool valid = sub_ok && (x < g.W) && (d >= g.dVLo) && (d <= g.dHi) && (x - d >= 0);
             // ASW: cost / tot (:88), one volume serves both references; GSW: un-normalised left / right sums
             const float cost = GSW ? c0[b] : __fdiv_rn(c0[b], c1[b]);
             out0[b] = valid ? (GSW ? c1[b] : cost) : INFINITY;
@@ -769,7 +783,7 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
             best = o < best ? o : best;
         }
         if ((lane & 7) == 0 && x < g.W && best != KEY_NONE) atomicMin(P.bestL + (size_t)rowo * g.W + x, best);
-        if (x < g.W) {
+        if (x < g.W && sub_ok) {
             const size_t o = ((size_t)rowo * g.W + x) * P.Dp + (size_t)ch * DC + kb;
             if (P.vol0) *reinterpret_cast<float4 *>(P.vol0 + o) = make_float4(out0[0], out0[1], out0[2], out0[3]);
             if (GSW && P.vol1) *reinterpret_cast<float4 *>(P.vol1 + o) = make_float4(out1[0], out1[1], out1[2], out1[3]);
@@ -937,6 +951,8 @@ struct Ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
     double agg_ms_done = 0;
     long long agg_launches = 0, total_launches = 0;
+    int sm_count = 148;
+    int blocks_per_sm = 1;           // of the aggregation kernel about to be launched (launch_agg)
     int last_kernel = 0;             // aggregation kernel of the last call: 1 = k_aggregate_tc, 2 = k_aggregate_ws (0: none yet)
     int last_dc = 0;                 // and its disparity chunk
     int smem_attr_ws[24] = {};       // largest dynamic-smem opt-in set so far, per k_aggregate_ws instantiation
@@ -1024,6 +1040,7 @@ int ctx_init(Ctx &c, int device) {
     if (prop.major < 10)
         return fail(SS_ERR_CUDA, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
                                      "; libsspassive is built for sm_100a only");
+    c.sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     float lut[256];
     for (int i = 0; i < 256; ++i) lut[i] = srgb_linear100(i);
     CU_TRY(cudaMemcpyToSymbol(c_lin100, lut, sizeof(lut)));
@@ -1161,34 +1178,56 @@ Geom make_geom(const Call &q, int DC) {
     return g;
 }
 
+// One aggregation pass = one launch over every (chunk, row, x tile) block -- or two when the last wave would leave most SMs
+// idle.  A block occupies a whole SM (shared memory, tensor memory), so `total` blocks take ceil(total / SMs) rounds; when
+// the last round holds fewer than a third of the SMs' worth of blocks (8-way row stripes of a KITTI frame: 611 blocks =
+// 4.13 rounds of 148) those tail tiles are launched separately with nsub = T/32: each block then handles ONE 32-column block
+// of its tile (one consumer warp per scheduler instead of three, 6 of the 10 weight column blocks), so the tail costs about
+// half a round.  Every (x, d) pair is still computed by the same instruction sequence: the maps do not change by a bit.
 template <typename K>
-int launch_agg(Ctx &c, K kernel, int &attr, int smem, const AggParams &P, int threads, cudaStream_t st) {
+int launch_agg(Ctx &c, K kernel, int &attr, int smem, AggParams P, int threads, cudaStream_t st) {
     if (smem > 227 * 1024) return fail(SS_ERR_PARAM, "winSize too large for the shared-memory tiling of the aggregation kernel");
     if (attr < smem) {
         CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = smem;
     }
-    dim3 grid(P.g.ntx, P.g.row1 - P.g.row0, P.g.nch);
+    const int total = P.g.ntx * (P.g.row1 - P.g.row0) * P.g.nch;
+    const int xb = P.g.T / 32;
+    int tail = c.blocks_per_sm == 1 ? total % c.sm_count : 0;       // only the one-block-per-SM kernels are wave-quantised this way
+    static const int split_off = [] { const char *e = getenv("SS_NO_TAIL_SPLIT"); return e ? atoi(e) : 0; }();
+    if (split_off || tail * xb > c.sm_count || total < c.sm_count) tail = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c.profile) {
         CU_TRY(cudaEventCreate(&e0));
         CU_TRY(cudaEventCreate(&e1));
         CU_TRY(cudaEventRecord(e0, st));
     }
-    kernel<<<grid, threads, smem, st>>>(P);
+    P.g.tile0 = 0;
+    P.g.nsub = 1;
+    kernel<<<dim3(total - tail, 1, 1), threads, smem, st>>>(P);
     CU_TRY(cudaGetLastError());
+    c.total_launches++;
+    if (tail) {
+        P.g.tile0 = total - tail;
+        P.g.nsub = xb;
+        kernel<<<dim3(tail, xb, 1), threads, smem, st>>>(P);
+        CU_TRY(cudaGetLastError());
+        c.total_launches++;
+    }
     if (c.profile) {
         CU_TRY(cudaEventRecord(e1, st));
         c.events.emplace_back(e0, e1);
     }
     c.agg_launches++;
-    c.total_launches++;
     return SS_OK;
 }
 
 template <bool GSW, int DC, int REM>
 int launch_ws_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
     const int di = ((DC == 128 ? 2 : (DC == 64 ? 1 : 0)) * 4 + REM / 2) * 2 + (GSW ? 1 : 0);
+    const int smem = ws_smem(P.g.win, DC, GSW).total;
+    // blocks per SM: register budget (WsCfg::MINB) and shared memory
+    c.blocks_per_sm = std::max(1, std::min((int)WsCfg<GSW, DC>::MINB, (227 * 1024) / (smem + 1024)));
     return launch_agg(c, k_aggregate_ws<GSW, DC, REM>, c.smem_attr_ws[di], ws_smem(P.g.win, DC, GSW).total, P, WsCfg<GSW, DC>::NT, st);
 }
 template <bool GSW, int DC>
@@ -1211,8 +1250,9 @@ int launch_ws(Ctx &c, const AggParams &P, cudaStream_t st) {
 // tensor memory; 39 < win: one stage (SINGLE).
 template <int REM, bool SINGLE>
 int launch_tc_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
+    c.blocks_per_sm = 1;
     return launch_agg(c, k_aggregate_tc<REM, SINGLE>, c.smem_attr_tc[(REM / 2) * 2 + (SINGLE ? 1 : 0)], tc_smem(P.g.win, SINGLE).total, P,
-                      512, st);
+                      TC_THREADS, st);
 }
 template <bool SINGLE>
 int launch_tc_s(Ctx &c, const AggParams &P, cudaStream_t st) {
@@ -1339,8 +1379,12 @@ int run_device(Ctx &c, const Call &q, const uint8_t *d_img1, const uint8_t *d_im
         P.vol1 = o.want_vol1 ? (float *)c.vol1.p : nullptr;
         P.Dp = Dp;
         P.vol_export = (o.want_vol0 || o.want_vol1) ? 1 : 0;
-        static const int freerun = [] { const char *e = getenv("SS_FREERUN"); return e ? atoi(e) : 0; }();
-        P.freerun = freerun;
+        {
+            // timing experiments (results are garbage): 1 k_aggregate_ws consumers free-running, producers idle;
+            // k_aggregate_tc: 2 producers tabulate nothing, 4 consumers accumulate nothing, 8 no tcgen05.mma
+            const char *e = getenv("SS_FREERUN");
+            P.freerun = e ? atoi(e) : 0;
+        }
 #ifdef SS_DEBUG_DUMP
         P.dbg = g_dbg;
 #endif
@@ -1570,8 +1614,7 @@ int ss_init_devices(const int *devices, int n) {
         if (L.rc) return L.rc;
     }
     std::lock_guard<std::mutex> lk(g_cfg_mu);
-    if (g_nccl.devs != devs) nccl_setup(devs);      // optional: only ss_*_compute_multi_device needs the communicators
-    g_devices = devs;
+    g_devices = devs;                               // the NCCL communicators are created by the first multi_device call
     cudaSetDevice(devs[0]);
     return SS_OK;
 }
@@ -1663,8 +1706,8 @@ static int multi_device(const Call &q0, const uint8_t *const *d_img1, const uint
     {
         std::lock_guard<std::mutex> lk(g_cfg_mu);
         devs = g_devices;
-        if (devs.size() > 1 && g_nccl.devs != devs)
-            return fail(SS_ERR_CUDA, "NCCL communicators are not available: " + (g_nccl.err.empty() ? std::string("call ss_init_devices first") : g_nccl.err));
+        if (devs.size() > 1 && g_nccl.devs != devs && nccl_setup(devs) != SS_OK)
+            return fail(SS_ERR_CUDA, "NCCL communicators are not available: " + g_nccl.err);
         comms = g_nccl.comms;
     }
     const int n = (int)devs.size();

@@ -418,6 +418,29 @@ def test_devices_kwarg_shards_rows_over_gpus_in_process():
         _cabi.use_devices([0])
 
 
+def test_tail_wave_split_is_bit_identical():
+    """A launch whose last wave would fill only a few SMs runs those tail tiles as 32-column sub-blocks (launch_agg in
+    csrc/ss_passive.cu).  150 tiles on 148 SMs -> 2 tail tiles x 3 sub-blocks; the two half-frame stripe calls (75 tiles each,
+    no split) must give the same bits, and the split call must pass the oracle check, cost volume included."""
+    l, r, _ = synth_pair(200, 50, 100, 71)
+    kw = dict(winSize=21, maxDisparity=100, minDisparity=0, gammaC=5.0, gammaP=17.5, consistent=True)
+    m = ss.passive.StereoASW(**kw)
+    full = m.compute_staged(l, r, cost=True)
+    ref = oracle.asw(l, r, stages=True, cost=True, **kw)
+    parity.check_cost(full["cost"], ref["cost"])
+    parity.check_staged(full, ref, ref["cost"], ref["cost"], 0, True, max_fraction=0.01)
+    halves = [m.compute_staged(l, r, cost=True, rows=rr) for rr in ((0, 25), (25, 50))]
+    for k in ("left", "right", "invalid", "final", "cost"):
+        assert np.array_equal(np.concatenate([h[k] for h in halves]), full[k]), k
+    # GSW (64-column tiles, 2 sub-blocks): 4 x 38 = 152 tiles
+    lg, rg, _ = synth_pair(200, 38, 100, 72)
+    g = ss.passive.StereoGSW(9, 100)
+    fullg = g.compute_staged(lg, rg, cost=True)
+    halvesg = [g.compute_staged(lg, rg, cost=True, rows=rr) for rr in ((0, 19), (19, 38))]
+    for k in ("left", "right", "invalid", "final", "cost_left", "cost_right"):
+        assert np.array_equal(np.concatenate([h[k] for h in halvesg]), fullg[k]), k
+
+
 def test_row_stripes_device_entry_point():
     import torch
     from simplestereo_b200 import _cabi
