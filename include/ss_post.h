@@ -57,8 +57,9 @@ int ss_remap_linear_device(const uint8_t *d_src, int src_width, int src_height, 
 /* simplestereo.points.exportPLY(points3D, filepath, referenceImage=None, precision=6) -- simplestereo/points.py:10-80.
  * Host-side ASCII writer, byte-identical to the reference's per-point Python loop, formatted on all host threads.
  * points: n x 3 float32 (points_are_double == 0) or float64; shape / ndims: the original array shape for the header
- * comment; bgr: optional n x 3 uint8 (written as R G B); intensity: optional n values, int64 (intensity_kind 1) or
- * float64 (2), used only when bgr is NULL. */
+ * comment; bgr: optional n x 3 uint8 (written as R G B); intensity: used only when bgr is NULL -- n values, int64
+ * (intensity_kind 1) or float64 (2), or n x 3 int64 B G R triples of a non-uint8 integer colour image (3: the
+ * reference formats them with "{:d}" whatever their range, points.py:53-55). */
 int ss_export_ply(const void *points, int points_are_double, long long n, const long long *shape, int ndims,
                   const uint8_t *bgr, const void *intensity, int intensity_kind, const char *path, int precision);
 

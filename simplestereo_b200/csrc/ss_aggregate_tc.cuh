@@ -31,8 +31,15 @@
 //     SINGLE (39 < win <= 79): one stage of A, 192 + 2 KC half + KC (hi|lo) + j with KC = 8 ceil(win / 8), and one stage of
 //     the left-weight residual in shared memory; the producers then wait for the previous row's MMAs (a second commit onto
 //     barrier 7) before they overwrite them -- a stall of one MMA batch per window row instead of a second buffer.
-//   * one thread (the utility warp: lane 0 of warp 16, which also drives the TMA copies) issues the 30 tcgen05.mma per
-//     window row and commits them onto the "weight stage free" mbarrier, whose count is consumers + 1.
+//   * two threads issue the 30 tcgen05.mma per window row -- lane 0 of producer 2 the 15 of accumulator half 0, lane 0 of
+//     producer 3 those of half 1 -- and commit them onto the "weight stage free" mbarrier, whose count is consumers + 2.
+
+#ifndef SS_TC_MMASPLIT
+#define SS_TC_MMASPLIT 1       // 1: producers 2 and 3 issue one accumulator half each; 0: producer 3 issues all (A/B timing builds)
+#endif
+#ifndef SS_TC_E16
+#define SS_TC_E16 1            // 1: bfloat16 raw costs for win <= 39; 0: bytes everywhere (A/B timing builds)
+#endif
 
 constexpr int TC_SBO = 144;                       // bytes between 8-column groups of the left-weight operand
 constexpr int TC_LBO = (TILE_WS / 8) * TC_SBO;    // bytes between the two 4-offset chunks of a K group
@@ -40,13 +47,32 @@ constexpr int TC_KGB = 2 * TC_LBO;                // bytes per K group (8 window
 constexpr int TC_DS_BYTES = 224 * TILE_WS * 4;    // denominators read back: [r][x]
 constexpr float TC_TRUNC_PER_MMA = 5.9604645e-8f;  // 2^-24: half the worst-case relative truncation loss of one tcgen05.mma
 
+// Raw costs in shared memory.  win <= 39: bfloat16 (the truncated AD is an integer <= 40: exact), 8 bytes per (column, 4
+// disparities) -> one LDS.64 and four ALU ops (shift / mask) turn them into the two float pairs the packed FMAs read.  The byte
+// form needs four I2F.U8 instead, which issue on the XU pipe at a quarter rate and share it with the producers' MUFU
+// (measured issue cost 1.7 cycles each against 0.6 for an ALU op); it remains for 39 < win, where shared memory is short.
+// Column pitch: 2 * 128 + 8 bytes (x-groups 8 columns apart land 64 bytes apart) / 128 + 4 bytes.
+__host__ __device__ constexpr int tc_ep(bool single) { return (single || !SS_TC_E16) ? 128 + 4 : 2 * 128 + 8; }
+
+// bfloat16 halves of a word -> float, as byte permutes (ALU pipe; a plain shift is compiled to IMAD on the FMA pipe)
+__device__ __forceinline__ float bf16_lo(uint32_t w) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(r) : "r"(w));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float bf16_hi(uint32_t w) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0, 0x3244;" : "=r"(r) : "r"(w));
+    return __uint_as_float(r);
+}
+
 struct TcSmem {
     int e, f1, f2, pa, c1, c2, w1, w2, ds, total;
     int ebytes, f1bytes, f2bytes, pabytes, w1arr, w2bytes;
 };
 // left-weight operand region: [hi stage 0 | hi stage 1 | lo stage 0 | lo stage 1 (absent when single)]
 __host__ __device__ inline TcSmem tc_smem(int win, bool single) {
-    const int T = TILE_WS, DC = 128, NU = T + win - 1, NR = T + DC - 1, NRp = T + DC, NV = NR + win - 1, EP = DC + 4;
+    const int T = TILE_WS, DC = 128, NU = T + win - 1, NR = T + DC - 1, NRp = T + DC, NV = NR + win - 1, EP = tc_ep(single);
     const int winq = (win + 3) >> 2, winr = winq * 4, KG = (win + 7) >> 3;
     TcSmem p;
     p.ebytes = (NU * EP + 15) & ~15;
@@ -82,11 +108,12 @@ __device__ __forceinline__ void tc_st4(uint32_t taddr, uint32_t a, uint32_t b, u
 }
 __device__ __forceinline__ float tc_lo(float w) { return __fsub_rn(w, __uint_as_float(__float_as_uint(w) & 0xffffe000u)); }
 
-constexpr int TC_THREADS = 544;                   // 12 consumer + 4 producer + 1 utility warp
+constexpr int TC_THREADS = 512;                   // 12 consumer + 4 producer warps: the whole register file at 128 per thread
 
 template <int REM, bool SINGLE>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams P) {
-    constexpr int DC = 128, T = TILE_WS, NRp = T + DC, EP = DC + 4, CW = 12, PW = 4, NDB = 4, NT = TC_THREADS;
+    constexpr int DC = 128, T = TILE_WS, NRp = T + DC, EP = tc_ep(SINGLE), CW = 12, PW = 4, NDB = 4, NT = TC_THREADS;
+    constexpr bool E16 = !SINGLE && SS_TC_E16;     // raw costs as bfloat16 (see tc_ep)
     extern __shared__ __align__(128) unsigned char smem[];
 
     const Geom &g = P.g;
@@ -135,12 +162,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
             mbar_init(BAR(1 + s), 1);
             mbar_init(BAR(3 + s), PW);
             mbar_init(BAR(5 + s), PW);
-            mbar_init(BAR(8 + s), CW + 1);
+            mbar_init(BAR(8 + s), CW + (SS_TC_MMASPLIT ? 2 : 1));
             mbar_init(BAR(11 + s), 1);
             mbar_init(BAR(13 + s), CW);
         }
         mbar_init(BAR(15), PW);
-        mbar_init(BAR(7), 1);
+        mbar_init(BAR(7), SS_TC_MMASPLIT ? 2 : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -152,17 +179,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
                       : 192u + (uint32_t)stage * 160u + (uint32_t)half * 80u + (uint32_t)lo * 40u;
     };
 
-    if (warp == CW + PW) {
-        // =================================== utility warp ===================================
-        // One lane drives every asynchronous engine of the block: the TMA bulk copies (features, proximity exponents, raw
-        // costs) and the tcgen05.mma batches.  It used to be a producer lane; measured on the B200 (SS_FREERUN=8): the issue
-        // of a row's 30 MMAs holds the issuing warp for about as long as they run (1.5 k cycles per window row), which
-        // delayed that producer's weights -- and with them the whole block -- by 11 %.
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-        if (lane != 0) return;
+    if (warp >= CW) {
+        // =================================== producers ===================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+        const int pw = warp - CW;
+        const uint32_t lane_base = (uint32_t)(pw * 32) << 16;       // this warp's quarter of the TMEM lanes
         const int f2_start = x0 - dlo - DC + 1 - pad + g.PL2;
         const int c2_start = x0 - dlo - DC + 1 + g.PL2;
         const size_t e_plane = (size_t)g.UW * EP;
+        const float4 *C1s = reinterpret_cast<const float4 *>(smem + sp.c1);
+        const float4 *C2s = reinterpret_cast<const float4 *>(smem + sp.c2);
+
         auto issue_F = [&](int n) {
             const int i = i_lo + n, ii = y - pad + i, st = n & 1;
             const uint32_t bar = BAR(1 + st);
@@ -179,57 +206,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
                         static_cast<const uint8_t *>(P.E) + ((size_t)ch * erows + (ii - g.erow0)) * e_plane + (size_t)x0 * EP,
                         (uint32_t)sp.ebytes, bar);
         };
-        mbar_expect_tx(BAR(0), (uint32_t)((T + NR) * 16));
-        tma_load_1d(smem_u32(smem + sp.c1), P.F1 + (size_t)(y - g.erow0) * g.UW + x0 + pad, T * 16, BAR(0));
-        tma_load_1d(smem_u32(smem + sp.c2), P.F2 + (size_t)(y - g.erow0) * g.VW + c2_start, NR * 16, BAR(0));
-        issue_F(0);
-        const uint32_t idesc = tc_idesc(128, T);
-        const int KGx = (P.freerun & 8) ? 0 : KG;         // timing experiment: no MMAs (the commits still arrive)
-        int sw = 0, phw = 0;
-        for (int n = 0; n < nsteps; ++n) {
-            const int st = n & 1, ph = (n >> 1) & 1;
-            if (n + 1 < nsteps) {
-                mbar_wait(BAR(3 + ((n + 1) & 1)), (((n + 1) >> 1) & 1) ^ 1);   // feature stage free
-                issue_F(n + 1);
-            }
-            mbar_wait(BAR(13 + st), ph ^ 1);                                   // raw-cost stage free
-            issue_E(n);
-            // ---- the tensor core: D[r][x] += W2hi*W1hi + W2hi*W1lo + W2lo*W1hi over this window row ----
-            mbar_wait(BAR(5 + sw), phw);                 // every producer has arrived: the operands of this row are in place
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t bhi = smem_u32(smem + sp.w1 + sw * sp.w1arr);
-            const uint32_t blo = smem_u32(smem + sp.w1 + (2 + (SINGLE ? 0 : sw)) * sp.w1arr);
-            for (int half = 0; half < 2; ++half)
-                for (int term = 0; term < 3; ++term) {
-                    const uint32_t a0 = tbase + colA(sw, half, term == 2);
-                    const uint32_t b0 = term == 1 ? blo : bhi;
-                    for (int kg = 0; kg < KGx; ++kg) {
-                        const u64 bd = tc_sdesc(b0 + (uint32_t)kg * TC_KGB, TC_LBO, TC_SBO);
-                        const uint32_t acc = !(n == 0 && term == 0 && kg == 0);
-                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tbase + 96u * half),
-                                     "r"(a0 + 8u * kg), "l"(bd), "r"(idesc), "r"(acc)
-                                     : "memory");
-                    }
-                }
-            // completion of everything issued so far arrives on "weight stage free" (and on barrier 7 when the operands are
-            // single-staged)
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(8 + sw)) : "memory");
-            if (SINGLE)
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(7)) : "memory");
-            if (++sw == 2) { sw = 0; phw ^= 1; }
+        if (pw == 0 && lane == 0) {
+            mbar_expect_tx(BAR(0), (uint32_t)((T + NR) * 16));
+            tma_load_1d(smem_u32(smem + sp.c1), P.F1 + (size_t)(y - g.erow0) * g.UW + x0 + pad, T * 16, BAR(0));
+            tma_load_1d(smem_u32(smem + sp.c2), P.F2 + (size_t)(y - g.erow0) * g.VW + c2_start, NR * 16, BAR(0));
+            issue_F(0);
         }
-        return;
-    }
-
-    if (warp >= CW) {
-        // =================================== producers ===================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        const int pw = warp - CW;
-        const uint32_t lane_base = (uint32_t)(pw * 32) << 16;       // this warp's quarter of the TMEM lanes
-        const float4 *C1s = reinterpret_cast<const float4 *>(smem + sp.c1);
-        const float4 *C2s = reinterpret_cast<const float4 *>(smem + sp.c2);
-
         // K padding: window offsets in [win, 8 KG) must contribute 0.  Zero every A column of this warp's TMEM lanes and
         // the whole left-weight operand once; offsets inside the last written batch are zeroed when they are written.
         for (int c = 0; c < (SINGLE ? (int)(4u * KC) : 320); c += 4) tc_st4(tbase + lane_base + 192u + c, 0u, 0u, 0u, 0u);
@@ -239,15 +221,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
         asm volatile("bar.sync 1, 128;" ::: "memory");              // the producers' own barrier: zeroing done everywhere
 
         const int NB = winq;                                        // batches of 4 window offsets per column block
-        // left-weight batches (3 column blocks x NB) are split so that every producer tabulates the same number of batches:
-        // producers 0-2 own two right-column blocks (cb = pw, pw + 4), producer 3 only one.
         // A block restricted to x-block xsub needs right centres r = T-1-x+k with x in the block (column blocks cbr0..cbr1)
         // and one left block; everything else stays at the zeros written below.
         const int cbr0 = xsub < 0 ? 0 : T / 32 - 1 - xsub, cbr1 = xsub < 0 ? NRp / 32 - 1 : (T - 1 - 32 * xsub + DC - 1) / 32;
+        // full tile: 7 right blocks (producers 0-2 two each, producer 3 one) + 3 left blocks = 10 NB batches; producers 2 and 3
+        // also issue the MMAs, so they take 9/4 NB each and producers 0, 1 take 11/4 NB: left shares 3/4, 3/4, 1/4, 5/4 NB
+#if SS_TC_MMASPLIT
+        const int l0 = xsub >= 0 ? xsub * NB + (pw * NB) / 4
+                                 : pw == 0 ? 0 : pw == 1 ? (NB * 3) / 4 : pw == 2 ? (NB * 6) / 4 : (NB * 7) / 4;
+        const int l1 = xsub >= 0 ? xsub * NB + ((pw + 1) * NB) / 4
+                                 : pw == 0 ? (NB * 3) / 4 : pw == 1 ? (NB * 6) / 4 : pw == 2 ? (NB * 7) / 4 : 3 * NB;
+#else
         const int l0 = xsub >= 0 ? xsub * NB + (pw * NB) / 4
                                  : pw == 0 ? 0 : pw == 1 ? (NB * 5) / 9 : pw == 2 ? (NB * 11) / 9 : (NB * 16) / 9;
         const int l1 = xsub >= 0 ? xsub * NB + ((pw + 1) * NB) / 4
                                  : pw == 0 ? (NB * 5) / 9 : pw == 1 ? (NB * 11) / 9 : pw == 2 ? (NB * 16) / 9 : 3 * NB;
+#endif
         const int l0_blk = l0 / NB, l0_jb = l0 - l0_blk * NB;
         const int o_f1 = sp.f1, o_f2 = sp.f2, o_pa = sp.pa, o_w1 = sp.w1, o_w2 = sp.w2;
         const int b_f1 = sp.f1bytes, b_f2 = sp.f2bytes, b_pa = sp.pabytes, b_w2 = sp.w2bytes, w1arr = sp.w1arr;
@@ -255,6 +244,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
         int sw = 0, phw = 0;
         for (int n = 0; n < nsteps; ++n) {
             const int st = n & 1, ph = (n >> 1) & 1;
+            if (pw == 0 && lane == 0) {
+                if (n + 1 < nsteps) {
+                    mbar_wait(BAR(3 + ((n + 1) & 1)), (((n + 1) >> 1) & 1) ^ 1);
+                    issue_F(n + 1);
+                }
+                mbar_wait(BAR(13 + st), ph ^ 1);
+                issue_E(n);
+            }
+            __syncwarp();
             if (n == 0) mbar_wait(BAR(0), 0);
             mbar_wait(BAR(1 + st), ph);            // features of this window row have landed
             mbar_wait(BAR(8 + sw), phw ^ 1);  // consumers AND the tensor core are done with this weight stage
@@ -330,6 +328,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
                 mbar_arrive(BAR(5 + sw));        // weights ready
                 mbar_arrive(BAR(3 + st));        // feature stage may be refilled
             }
+            // ---- the tensor core: D[r][x] += W2hi*W1hi + W2hi*W1lo + W2lo*W1hi over this window row ----
+            // The issue of a row's 30 MMAs holds the issuing lane for about as long as they run (measured: SS_FREERUN=8 removes
+            // 11 % of the kernel time), so it is split: producer 2 issues the MMAs of accumulator half 0, producer 3 those of
+            // half 1 -- each half is still accumulated in program order by ONE thread, hence bit-reproducible.
+            if (pw >= (SS_TC_MMASPLIT ? 2 : 3)) {
+                mbar_wait(BAR(5 + sw), phw);     // every producer has arrived: the operands of this row are in place
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const int KGx = (P.freerun & 8) ? 0 : KG;     // timing experiment: no MMAs (the commits still arrive)
+                    const uint32_t idesc = tc_idesc(128, T);
+                    const uint32_t bhi = smem_u32(W1hi), blo = smem_u32(W1lo);
+                    for (int half = SS_TC_MMASPLIT ? pw - 2 : 0; half < (SS_TC_MMASPLIT ? pw - 1 : 2); ++half)
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t a0 = tbase + colA(sw, half, term == 2);
+                        const uint32_t b0 = term == 1 ? blo : bhi;
+                        for (int kg = 0; kg < KGx; ++kg) {
+                            const u64 bd = tc_sdesc(b0 + (uint32_t)kg * TC_KGB, TC_LBO, TC_SBO);
+                            const uint32_t acc = !(n == 0 && term == 0 && kg == 0);
+                            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tbase + 96u * half),
+                                         "r"(a0 + 8u * kg), "l"(bd), "r"(idesc), "r"(acc)
+                                         : "memory");
+                        }
+                    }
+                    // completion of everything this thread issued so far arrives on "weight stage free" (and on barrier 7 when
+                    // the operands are single-staged)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(8 + sw)) : "memory");
+                    if (SINGLE)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(7)) : "memory");
+                }
+                __syncwarp();
+            }
             if (++sw == 2) { sw = 0; phw ^= 1; }
         }
         // ---- denominators: TMEM -> shared memory [r][x] once the last window row is fully consumed and accumulated ----
@@ -385,11 +415,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
         mbar_wait(BAR(11 + st), ph);             // raw costs of this window row
         if (warp_live && !(P.freerun & 4)) {
             u64 ring[8][2];
-            const uint8_t *ep = smem + (sp.e + st * sp.ebytes) + xb * EP + kb;
+            const uint8_t *ep = smem + (sp.e + st * sp.ebytes) + xb * EP + kb * (E16 ? 2 : 1);
             auto load_e = [&](const uint8_t *q, u64 &lo, u64 &hi) {
-                const uint32_t e = *reinterpret_cast<const uint32_t *>(q);
-                lo = pk(u8_to_f32(e, 0), u8_to_f32(e, 1));
-                hi = pk(u8_to_f32(e, 2), u8_to_f32(e, 3));
+                if (E16) {
+                    const uint2 e = *reinterpret_cast<const uint2 *>(q);       // 4 bfloat16: float = bits << 16
+                    lo = pk(bf16_lo(e.x), bf16_hi(e.x));
+                    hi = pk(bf16_lo(e.y), bf16_hi(e.y));
+                } else {
+                    const uint32_t e = *reinterpret_cast<const uint32_t *>(q);
+                    lo = pk(u8_to_f32(e, 0), u8_to_f32(e, 1));
+                    hi = pk(u8_to_f32(e, 2), u8_to_f32(e, 3));
+                }
             };
 #pragma unroll
             for (int a = 0; a < 7; ++a) load_e(ep + a * EP, ring[a][0], ring[a][1]);

@@ -356,15 +356,21 @@ namespace {
 
 // Python's "{:.{p}f}".format(v): correctly rounded like glibc's printf, but nan never carries a sign
 inline void ply_fmt(std::string &o, double v, int precision, int width) {
-    char buf[400];
-    if (std::isnan(v)) {
-        snprintf(buf, sizeof(buf), "%*s", width, "nan");
-    } else if (width >= 0) {
-        snprintf(buf, sizeof(buf), "%*f", width, v);               // "{:{p}f}": width p, default precision 6 (points.py:77)
-    } else {
-        snprintf(buf, sizeof(buf), "%.*f", precision, v);
+    char buf[64];
+    const char *fmt = width >= 0 ? "%*f" : "%.*f";                  // "{:{p}f}": width p, default precision 6 (points.py:77)
+    const int arg = width >= 0 ? width : precision;
+    int n;
+    if (std::isnan(v)) n = snprintf(buf, sizeof(buf), "%*s", width >= 0 ? width : 0, "nan");
+    else n = snprintf(buf, sizeof(buf), fmt, arg, v);
+    if (n < (int)sizeof(buf)) {
+        o.append(buf, (size_t)std::max(n, 0));
+        return;
     }
-    o += buf;
+    // large magnitudes / precisions (up to 300 decimals of a 1e308 double): format into a buffer of the exact size
+    std::string big((size_t)n + 1, '\0');
+    if (std::isnan(v)) snprintf(&big[0], big.size(), "%*s", width >= 0 ? width : 0, "nan");
+    else snprintf(&big[0], big.size(), fmt, arg, v);
+    o.append(big.data(), (size_t)n);
 }
 
 }  // namespace
@@ -374,13 +380,14 @@ extern "C" int ss_export_ply(const void *points, int points_are_double, long lon
                              int precision) {
     if (!points || !path || n < 0 || ndims < 0 || (ndims > 0 && !shape) || precision < 0 || precision > 300)
         return fail(SS_ERR_FORMAT, "Invalid input format!");
-    if (intensity && intensity_kind != 1 && intensity_kind != 2) return fail(SS_ERR_FORMAT, "Invalid input format!");
+    if (intensity && (intensity_kind < 1 || intensity_kind > 3)) return fail(SS_ERR_FORMAT, "Invalid input format!");
+    const bool bgr64 = !bgr && intensity && intensity_kind == 3;    // BGR triples of a non-uint8 integer image, as int64
     FILE *f = fopen(path, "w");
     if (!f) return fail(SS_ERR_PARAM, std::string("cannot open ") + path + " for writing");
     std::string hdr = "ply\nformat ascii 1.0\ncomment SimpleStereo point cloud export\ncomment Original array shape ";
     for (int k = 0; k < ndims; ++k) hdr += (k ? "x" : "") + std::to_string(shape[k]);
     hdr += "\nelement vertex " + std::to_string(n) + "\nproperty double x\nproperty double y\nproperty double z\n";
-    if (bgr) hdr += "property uchar red\nproperty uchar green\nproperty uchar blue\n";
+    if (bgr || bgr64) hdr += "property uchar red\nproperty uchar green\nproperty uchar blue\n";
     else if (intensity) hdr += intensity_kind == 1 ? "property int intensity\n" : "property float intensity\n";
     hdr += "end_header\n";
     fwrite(hdr.data(), 1, hdr.size(), f);
@@ -410,6 +417,11 @@ extern "C" int ss_export_ply(const void *points, int points_are_double, long lon
                         o += ' '; o += std::to_string((int)bgr[3 * i + 2]);
                         o += ' '; o += std::to_string((int)bgr[3 * i + 1]);
                         o += ' '; o += std::to_string((int)bgr[3 * i + 0]);
+                    } else if (bgr64) {                            // "{:d}" of whatever the integers hold (points.py:53-55)
+                        const long long *c = static_cast<const long long *>(intensity) + 3 * i;
+                        o += ' '; o += std::to_string(c[2]);
+                        o += ' '; o += std::to_string(c[1]);
+                        o += ' '; o += std::to_string(c[0]);
                     } else if (intensity && intensity_kind == 1) {
                         o += ' '; o += std::to_string(static_cast<const long long *>(intensity)[i]);
                     } else if (intensity) {

@@ -123,9 +123,12 @@ def exportPLY(points3D, filepath, referenceImage=None, precision=6):
     if referenceImage is not None:
         referenceImage = np.asarray(referenceImage)
         if referenceImage.size == points3D.size:
-            if referenceImage.dtype != np.uint8:
-                raise TypeError("Wrong type input!")                # "property uchar": BGR images are uint8
-            bgr = np.ascontiguousarray(referenceImage.reshape(-1, 3))
+            if referenceImage.dtype == np.uint8:
+                bgr = np.ascontiguousarray(referenceImage.reshape(-1, 3))
+            elif np.issubdtype(referenceImage.dtype, np.integer):     # "{:d}" accepts any integer image (points.py:53-55)
+                inten, kind = np.ascontiguousarray(referenceImage.reshape(-1, 3), dtype=np.int64), 3
+            else:                                                     # "{:d}" of a float raises ValueError upstream
+                raise ValueError(f"Unknown format code 'd' for object of type '{referenceImage.dtype}'")
         else:
             inten = np.ravel(referenceImage)
             if inten.size != n:
@@ -146,14 +149,13 @@ def importPLY(filename, *properties):
     array with one row per vertex and one column per requested property, in the requested order.
     """
     cols = properties if properties else (0, 1, 2)
-    with open(filename, "r") as f:
-        text = f.read()
-    head, sep, body = text.partition("end_header\n")
-    if not sep:                                   # tolerate other capitalisation / trailing blanks, as the reference does
-        lines = text.splitlines()
-        k = next(i for i, ln in enumerate(lines) if ln.rstrip().lower() == "end_header")
-        body = "\n".join(lines[k + 1:])
-    rows = [ln.split(" ") for ln in body.splitlines()]
+    with open(filename, "r") as f:                # the reference's own scan: whole stripped lines, any capitalisation
+        for line in f:
+            if line.rstrip().lower() == "end_header":
+                break
+        rows = [ln.split(" ") for ln in f]        # no end_header: nothing is left to read, as upstream
+    if not rows:
+        return np.asarray([], dtype=float)
     out = np.empty((len(rows), len(cols)), dtype=float)
     for i, fields in enumerate(rows):
         for j, c in enumerate(cols):

@@ -44,3 +44,36 @@ def test_large_cloud_is_written_in_order(tmp_path):
 def test_unwritable_path_raises(tmp_path):
     with pytest.raises(ValueError):
         ss.points.exportPLY(np.zeros((2, 3), np.float32), str(tmp_path / "no_such_dir" / "x.ply"))
+
+
+def test_import_scans_whole_lines_like_the_reference(tmp_path):
+    """points.py:108-111 compares each stripped, lower-cased LINE with "end_header": a comment that merely contains the
+    token is not the end of the header; without any end_header line nothing is left to read (empty array, no exception)."""
+    p = tmp_path / "c.ply"
+    p.write_text("ply\nformat ascii 1.0\ncomment not the end_header\nelement vertex 2\nproperty double x\nEND_HEADER  \n1 2 3\n4 5 6\n")
+    assert np.array_equal(ss.points.importPLY(str(p)), [[1, 2, 3], [4, 5, 6]])
+    q = tmp_path / "n.ply"
+    q.write_text("ply\nformat ascii 1.0\nelement vertex 1\n1 2 3\n")
+    out = ss.points.importPLY(str(q))
+    assert out.shape == (0,) and out.dtype == float
+
+
+def test_export_integer_colour_images_and_extreme_precision(tmp_path):
+    """The reference formats colour triples with "{:d}" (points.py:53-55): any integer dtype goes, floats raise ValueError.
+    Coordinates are "{:.{p}f}" for any p: a 1e300 double at 300 decimals is 600 characters."""
+    pts = np.array([[1.5, -2.25, 3.0], [1e300, -1e-300, 0.1]], np.float64)
+    img = np.array([[300, -7, 65536], [1, 2, 3]], np.int32)
+    p = tmp_path / "i.ply"
+    ss.points.exportPLY(pts, str(p), img, precision=2)
+    body = p.read_text().split("end_header\n")[1].splitlines()
+    assert body[0] == "{:.2f} {:.2f} {:.2f} {:d} {:d} {:d}".format(1.5, -2.25, 3.0, 65536, -7, 300)
+    assert body[1] == "{:.2f} {:.2f} {:.2f} {:d} {:d} {:d}".format(1e300, -1e-300, 0.1, 3, 2, 1)
+    with pytest.raises(ValueError):
+        ss.points.exportPLY(pts, str(p), img.astype(np.float32))
+    ss.points.exportPLY(pts, str(p), precision=300)
+    body = p.read_text().split("end_header\n")[1].splitlines()
+    assert body[1] == "{:.300f} {:.300f} {:.300f}".format(1e300, -1e-300, 0.1)
+    g = np.array([0.5, 1e30])                                        # "{:{p}f}": width p, 6 decimals
+    ss.points.exportPLY(pts, str(p), g, precision=3)
+    body = p.read_text().split("end_header\n")[1].splitlines()
+    assert body[1].split(" ")[-1] == "{:3f}".format(1e30)

@@ -31,7 +31,7 @@ __global__ void k_pat(unsigned* out, int pat) {
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             unsigned a, b, c, d;
-            const unsigned ad = addr + k * step;
+            const unsigned ad = addr + k * step + ((it & 1) << 15);   // two alternating regions: keeps the loads inside the loop
             if (width == 16) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(ad));
             else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a) : "r"(ad));
             acc += a;
