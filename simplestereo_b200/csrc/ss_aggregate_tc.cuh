@@ -31,14 +31,18 @@
 //     SINGLE (39 < win <= 79): one stage of A, 192 + 2 KC half + KC (hi|lo) + j with KC = 8 ceil(win / 8), and one stage of
 //     the left-weight residual in shared memory; the producers then wait for the previous row's MMAs (a second commit onto
 //     barrier 7) before they overwrite them -- a stall of one MMA batch per window row instead of a second buffer.
-//   * two threads issue the 30 tcgen05.mma per window row -- lane 0 of producer 2 the 15 of accumulator half 0, lane 0 of
-//     producer 3 those of half 1 -- and commit them onto the "weight stage free" mbarrier, whose count is consumers + 2.
+//   * one thread (producer 3, lane 0) issues the 30 tcgen05.mma per window row and commits them onto the "weight stage
+//     free" mbarrier, whose count is consumers + 1.
 
-#ifndef SS_TC_MMASPLIT
-#define SS_TC_MMASPLIT 1       // 1: producers 2 and 3 issue one accumulator half each; 0: producer 3 issues all (A/B timing builds)
+#ifndef SS_TC_MMA_DEFER
+#define SS_TC_MMA_DEFER 1      // 1: a row's MMAs are issued two at a time between the NEXT row's weight batches; 0: in one burst
 #endif
-#ifndef SS_TC_E16
-#define SS_TC_E16 1            // 1: bfloat16 raw costs for win <= 39; 0: bytes everywhere (A/B timing builds)
+#ifndef SS_TC_CREG
+#define SS_TC_CREG 136         // registers per consumer / producer thread after setmaxnreg: 12 * CREG + 4 * PREG = 16 * 128
+#define SS_TC_PREG 96
+#endif
+#ifndef SS_TC_PUNROLL
+#define SS_TC_PUNROLL 2        // weight batches (of 4) in flight per producer lane in the right-column loop
 #endif
 
 constexpr int TC_SBO = 144;                       // bytes between 8-column groups of the left-weight operand
@@ -47,32 +51,13 @@ constexpr int TC_KGB = 2 * TC_LBO;                // bytes per K group (8 window
 constexpr int TC_DS_BYTES = 224 * TILE_WS * 4;    // denominators read back: [r][x]
 constexpr float TC_TRUNC_PER_MMA = 5.9604645e-8f;  // 2^-24: half the worst-case relative truncation loss of one tcgen05.mma
 
-// Raw costs in shared memory.  win <= 39: bfloat16 (the truncated AD is an integer <= 40: exact), 8 bytes per (column, 4
-// disparities) -> one LDS.64 and four ALU ops (shift / mask) turn them into the two float pairs the packed FMAs read.  The byte
-// form needs four I2F.U8 instead, which issue on the XU pipe at a quarter rate and share it with the producers' MUFU
-// (measured issue cost 1.7 cycles each against 0.6 for an ALU op); it remains for 39 < win, where shared memory is short.
-// Column pitch: 2 * 128 + 8 bytes (x-groups 8 columns apart land 64 bytes apart) / 128 + 4 bytes.
-__host__ __device__ constexpr int tc_ep(bool single) { return (single || !SS_TC_E16) ? 128 + 4 : 2 * 128 + 8; }
-
-// bfloat16 halves of a word -> float, as byte permutes (ALU pipe; a plain shift is compiled to IMAD on the FMA pipe)
-__device__ __forceinline__ float bf16_lo(uint32_t w) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(r) : "r"(w));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ float bf16_hi(uint32_t w) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, 0, 0x3244;" : "=r"(r) : "r"(w));
-    return __uint_as_float(r);
-}
-
 struct TcSmem {
     int e, f1, f2, pa, c1, c2, w1, w2, ds, total;
     int ebytes, f1bytes, f2bytes, pabytes, w1arr, w2bytes;
 };
 // left-weight operand region: [hi stage 0 | hi stage 1 | lo stage 0 | lo stage 1 (absent when single)]
 __host__ __device__ inline TcSmem tc_smem(int win, bool single) {
-    const int T = TILE_WS, DC = 128, NU = T + win - 1, NR = T + DC - 1, NRp = T + DC, NV = NR + win - 1, EP = tc_ep(single);
+    const int T = TILE_WS, DC = 128, NU = T + win - 1, NR = T + DC - 1, NRp = T + DC, NV = NR + win - 1, EP = DC + 4;
     const int winq = (win + 3) >> 2, winr = winq * 4, KG = (win + 7) >> 3;
     TcSmem p;
     p.ebytes = (NU * EP + 15) & ~15;
@@ -108,12 +93,14 @@ __device__ __forceinline__ void tc_st4(uint32_t taddr, uint32_t a, uint32_t b, u
 }
 __device__ __forceinline__ float tc_lo(float w) { return __fsub_rn(w, __uint_as_float(__float_as_uint(w) & 0xffffe000u)); }
 
-constexpr int TC_THREADS = 512;                   // 12 consumer + 4 producer warps: the whole register file at 128 per thread
+// 12 consumer + 4 producer warps = the whole register file at 128 per thread, re-split 136 / 96 by setmaxnreg.  (A 17th warp
+// for the TMA / MMA issue was tried: ptxas sizes a 544-thread launch at 96 registers per thread, the pool then holds
+// 17 * 32 * 96 and the consumers' setmaxnreg.inc to 136 never completes -- the kernel hangs.)
+constexpr int TC_THREADS = 512;
 
 template <int REM, bool SINGLE>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams P) {
-    constexpr int DC = 128, T = TILE_WS, NRp = T + DC, EP = tc_ep(SINGLE), CW = 12, PW = 4, NDB = 4, NT = TC_THREADS;
-    constexpr bool E16 = !SINGLE && SS_TC_E16;     // raw costs as bfloat16 (see tc_ep)
+    constexpr int DC = 128, T = TILE_WS, NRp = T + DC, EP = DC + 4, CW = 12, PW = 4, NDB = 4, NT = TC_THREADS;
     extern __shared__ __align__(128) unsigned char smem[];
 
     const Geom &g = P.g;
@@ -162,12 +149,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
             mbar_init(BAR(1 + s), 1);
             mbar_init(BAR(3 + s), PW);
             mbar_init(BAR(5 + s), PW);
-            mbar_init(BAR(8 + s), CW + (SS_TC_MMASPLIT ? 2 : 1));
+            mbar_init(BAR(8 + s), CW + 1);
             mbar_init(BAR(11 + s), 1);
             mbar_init(BAR(13 + s), CW);
         }
         mbar_init(BAR(15), PW);
-        mbar_init(BAR(7), SS_TC_MMASPLIT ? 2 : 1);
+        mbar_init(BAR(7), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -181,7 +168,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
 
     if (warp >= CW) {
         // =================================== producers ===================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SS_TC_PREG));
         const int pw = warp - CW;
         const uint32_t lane_base = (uint32_t)(pw * 32) << 16;       // this warp's quarter of the TMEM lanes
         const int f2_start = x0 - dlo - DC + 1 - pad + g.PL2;
@@ -224,22 +211,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
         // A block restricted to x-block xsub needs right centres r = T-1-x+k with x in the block (column blocks cbr0..cbr1)
         // and one left block; everything else stays at the zeros written below.
         const int cbr0 = xsub < 0 ? 0 : T / 32 - 1 - xsub, cbr1 = xsub < 0 ? NRp / 32 - 1 : (T - 1 - 32 * xsub + DC - 1) / 32;
-        // full tile: 7 right blocks (producers 0-2 two each, producer 3 one) + 3 left blocks = 10 NB batches; producers 2 and 3
-        // also issue the MMAs, so they take 9/4 NB each and producers 0, 1 take 11/4 NB: left shares 3/4, 3/4, 1/4, 5/4 NB
-#if SS_TC_MMASPLIT
-        const int l0 = xsub >= 0 ? xsub * NB + (pw * NB) / 4
-                                 : pw == 0 ? 0 : pw == 1 ? (NB * 3) / 4 : pw == 2 ? (NB * 6) / 4 : (NB * 7) / 4;
-        const int l1 = xsub >= 0 ? xsub * NB + ((pw + 1) * NB) / 4
-                                 : pw == 0 ? (NB * 3) / 4 : pw == 1 ? (NB * 6) / 4 : pw == 2 ? (NB * 7) / 4 : 3 * NB;
-#else
+        // full tile: 7 right blocks (producers 0-2 two each, producer 3 one) + 3 left blocks; producer 3 also issues the MMAs and
+        // takes 20 of the 90 batches of a 35-wide window (the others 23-24): left shares 5/9, 6/9, 5/9, 11/9 NB
         const int l0 = xsub >= 0 ? xsub * NB + (pw * NB) / 4
                                  : pw == 0 ? 0 : pw == 1 ? (NB * 5) / 9 : pw == 2 ? (NB * 11) / 9 : (NB * 16) / 9;
         const int l1 = xsub >= 0 ? xsub * NB + ((pw + 1) * NB) / 4
                                  : pw == 0 ? (NB * 5) / 9 : pw == 1 ? (NB * 11) / 9 : pw == 2 ? (NB * 16) / 9 : 3 * NB;
-#endif
         const int l0_blk = l0 / NB, l0_jb = l0 - l0_blk * NB;
         const int o_f1 = sp.f1, o_f2 = sp.f2, o_pa = sp.pa, o_w1 = sp.w1, o_w2 = sp.w2;
         const int b_f1 = sp.f1bytes, b_f2 = sp.f2bytes, b_pa = sp.pabytes, b_w2 = sp.w2bytes, w1arr = sp.w1arr;
+
+        // ---- the tensor core: D[r][x] += W2hi*W1hi + W2hi*W1lo + W2lo*W1hi per window row, issued by lane 0 of producer 3 ----
+        // (Measured on the B200: without the MMAs the kernel is 9 % faster, SS_FREERUN=8 -- issued in one burst, a row's 30 MMAs
+        // hold the issuing scheduler for about as long as they run.  Splitting the burst over two producers, one accumulator
+        // half each, measured 2 % SLOWER; a 17th warp for it cannot get registers, see TC_THREADS.)  With double-staged operands
+        // the MMAs of row n are therefore DEFERRED: they are issued two at a time between producer 3's weight batches of row
+        // n + 1, so the tensor pipe never backs up into the issue slot.  Each accumulator half is still fed in program order by
+        // one thread: bit-reproducible.
+        constexpr bool DEFER = SS_TC_MMA_DEFER && !SINGLE;
+        constexpr int PUNROLL = SS_TC_PUNROLL;
+        const int MM = 6 * KG;                                   // MMAs per window row: 2 halves x 3 terms x KG
+        int mm_row = -1, mm_done = 0, mm_stage = 0;              // pending row (producer 3; uniform across the warp)
+        auto mma_one = [&](int row, int stage, int m) {          // lane 0 only
+            const int half = m / (3 * KG), t = m - half * 3 * KG, term = t / KG, kg = t - term * KG;
+            const uint32_t bhi = smem_u32(smem + sp.w1 + stage * sp.w1arr);
+            const uint32_t blo = smem_u32(smem + sp.w1 + (2 + (SINGLE ? 0 : stage)) * sp.w1arr);
+            const uint32_t a0 = tbase + colA(stage, half, term == 2);
+            const u64 bd = tc_sdesc((term == 1 ? blo : bhi) + (uint32_t)kg * TC_KGB, TC_LBO, TC_SBO);
+            const uint32_t acc = !(row == 0 && term == 0 && kg == 0);
+            if (!(P.freerun & 8))                                // timing experiment: no MMAs (the commits still arrive)
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tbase + 96u * half),
+                             "r"(a0 + 8u * kg), "l"(bd), "r"(tc_idesc(128, T)), "r"(acc)
+                             : "memory");
+        };
+        auto mma_pump = [&](int k) {                             // issue up to k MMAs of the pending row; commit after the last
+            if (mm_row < 0) return;
+            const int upto = min(MM, mm_done + k);
+            if (lane == 0) {
+                for (int m = mm_done; m < upto; ++m) mma_one(mm_row, mm_stage, m);
+                if (upto == MM) {
+                    // completion of everything issued so far arrives on "weight stage free" (and on barrier 7 when the
+                    // operands are single-staged)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(8 + mm_stage)) : "memory");
+                    if (SINGLE)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(7)) : "memory");
+                }
+            }
+            __syncwarp();
+            mm_done = upto;
+            if (upto == MM) mm_row = -1;
+        };
 
         int sw = 0, phw = 0;
         for (int n = 0; n < nsteps; ++n) {
@@ -257,6 +279,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
             mbar_wait(BAR(1 + st), ph);            // features of this window row have landed
             mbar_wait(BAR(8 + sw), phw ^ 1);  // consumers AND the tensor core are done with this weight stage
             if (SINGLE && n > 0) mbar_wait(BAR(7), (n - 1) & 1);   // single-stage operands: the previous row's MMAs have read them
+            if (DEFER && pw == 3 && n > 0) {
+                mbar_wait(BAR(5 + (sw ^ 1)), sw == 0 ? phw ^ 1 : phw);   // every producer has finished the previous row
+                mm_row = n - 1; mm_done = 0; mm_stage = sw ^ 1;
+            }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
             const float4 *f1 = reinterpret_cast<const float4 *>(smem + o_f1 + st * b_f1);
@@ -276,7 +302,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
                 const float4 *nb = f2 + src;
                 float *dst = W2s + col;
                 const uint32_t ta = tbase + lane_base + colA(sw, cb >> 2, 0);
-#pragma unroll 2
+#pragma unroll PUNROLL
                 for (int jb = 0; jb < NB; ++jb) {
                     const float4 t = *reinterpret_cast<const float4 *>(parg + 4 * jb);
                     const float4 n0 = nb[0], n1 = nb[1], n2 = nb[2], n3 = nb[3];
@@ -295,6 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
                            __float_as_uint(tc_lo(w3)));
                     nb += 4;
                     dst += 4 * NRp;
+                    if (DEFER && pw == 3) mma_pump(2);
                 }
             }
             // ---- left columns: K-major operand shared by the consumers and the tensor core (hi) + its residual (lo) ----
@@ -319,7 +346,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
                 *reinterpret_cast<float4 *>(W1hi + qo) = make_float4(w0, w1, w2, w3);
                 *reinterpret_cast<float4 *>(W1lo + qo) = make_float4(tc_lo(w0), tc_lo(w1), tc_lo(w2), tc_lo(w3));
                 if (++jb == NB) { jb = 0; ++blk; }
+                if (DEFER && pw == 3) mma_pump(2);
             }
+            if (DEFER && pw == 3) mma_pump(MM);                      // whatever is left of the previous row
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> tensor-core (async proxy) reads
@@ -329,42 +358,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
                 mbar_arrive(BAR(3 + st));        // feature stage may be refilled
             }
             // ---- the tensor core: D[r][x] += W2hi*W1hi + W2hi*W1lo + W2lo*W1hi over this window row ----
-            // The issue of a row's 30 MMAs holds the issuing lane for about as long as they run (measured: SS_FREERUN=8 removes
-            // 11 % of the kernel time), so it is split: producer 2 issues the MMAs of accumulator half 0, producer 3 those of
-            // half 1 -- each half is still accumulated in program order by ONE thread, hence bit-reproducible.
-            if (pw >= (SS_TC_MMASPLIT ? 2 : 3)) {
+            if (pw == 3 && !DEFER) {                                 // burst: this row's MMAs right away
                 mbar_wait(BAR(5 + sw), phw);     // every producer has arrived: the operands of this row are in place
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const int KGx = (P.freerun & 8) ? 0 : KG;     // timing experiment: no MMAs (the commits still arrive)
-                    const uint32_t idesc = tc_idesc(128, T);
-                    const uint32_t bhi = smem_u32(W1hi), blo = smem_u32(W1lo);
-                    for (int half = SS_TC_MMASPLIT ? pw - 2 : 0; half < (SS_TC_MMASPLIT ? pw - 1 : 2); ++half)
-                    for (int term = 0; term < 3; ++term) {
-                        const uint32_t a0 = tbase + colA(sw, half, term == 2);
-                        const uint32_t b0 = term == 1 ? blo : bhi;
-                        for (int kg = 0; kg < KGx; ++kg) {
-                            const u64 bd = tc_sdesc(b0 + (uint32_t)kg * TC_KGB, TC_LBO, TC_SBO);
-                            const uint32_t acc = !(n == 0 && term == 0 && kg == 0);
-                            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tbase + 96u * half),
-                                         "r"(a0 + 8u * kg), "l"(bd), "r"(idesc), "r"(acc)
-                                         : "memory");
-                        }
-                    }
-                    // completion of everything this thread issued so far arrives on "weight stage free" (and on barrier 7 when
-                    // the operands are single-staged)
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(8 + sw)) : "memory");
-                    if (SINGLE)
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(7)) : "memory");
-                }
-                __syncwarp();
+                mm_row = n; mm_done = 0; mm_stage = sw;
+                mma_pump(MM);
             }
             if (++sw == 2) { sw = 0; phw ^= 1; }
         }
         // ---- denominators: TMEM -> shared memory [r][x] once the last window row is fully consumed and accumulated ----
         {
             const int swl = sw ^ 1, phl = sw == 0 ? phw ^ 1 : phw;   // stage / phase of the last window row
+            if (DEFER && pw == 3) {                                  // its MMAs are still to be issued
+                mbar_wait(BAR(5 + swl), phl);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                mm_row = nsteps - 1; mm_done = 0; mm_stage = swl;
+                mma_pump(MM);
+            }
             mbar_wait(BAR(8 + swl), phl);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float *Ds = reinterpret_cast<float *>(smem + sp.ds);
@@ -394,7 +404,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
     }
 
     // =================================== consumers ===================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SS_TC_CREG));
     const int xl = lane >> 3, dl = lane & 7;
     const int xg = (warp / NDB) * 4 + xl;
     const int dg = ((warp % NDB) * 8 + dl + 2 * xl) % (DC / 4);
@@ -415,17 +425,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
         mbar_wait(BAR(11 + st), ph);             // raw costs of this window row
         if (warp_live && !(P.freerun & 4)) {
             u64 ring[8][2];
-            const uint8_t *ep = smem + (sp.e + st * sp.ebytes) + xb * EP + kb * (E16 ? 2 : 1);
+            const uint8_t *ep = smem + (sp.e + st * sp.ebytes) + xb * EP + kb;
             auto load_e = [&](const uint8_t *q, u64 &lo, u64 &hi) {
-                if (E16) {
-                    const uint2 e = *reinterpret_cast<const uint2 *>(q);       // 4 bfloat16: float = bits << 16
-                    lo = pk(bf16_lo(e.x), bf16_hi(e.x));
-                    hi = pk(bf16_lo(e.y), bf16_hi(e.y));
-                } else {
-                    const uint32_t e = *reinterpret_cast<const uint32_t *>(q);
-                    lo = pk(u8_to_f32(e, 0), u8_to_f32(e, 1));
-                    hi = pk(u8_to_f32(e, 2), u8_to_f32(e, 3));
-                }
+                const uint32_t e = *reinterpret_cast<const uint32_t *>(q);
+                lo = pk(u8_to_f32(e, 0), u8_to_f32(e, 1));
+                hi = pk(u8_to_f32(e, 2), u8_to_f32(e, 3));
             };
 #pragma unroll
             for (int a = 0; a < 7; ++a) load_e(ep + a * EP, ring[a][0], ring[a][1]);

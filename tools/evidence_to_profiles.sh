@@ -5,13 +5,14 @@ set -eu
 T=${1:-r01}
 O=gpurun_out
 P=profiles
-for k in asw_ws gsw_ws; do
+for k in asw_tc gsw_ws; do
   [ -f $O/$k.ncu-rep ] || continue
   ncu -i $O/$k.ncu-rep --page raw --csv > $O/$k.raw.csv
-  if [ $k = asw_ws ]; then python tools/ncu_summary.py $O/$k.raw.csv $P/${T}_ncu_k_aggregate_ws_${k%_ws}.md $P/ncu_traffic.json > /dev/null
+  if [ $k = asw_tc ]; then python tools/ncu_summary.py $O/$k.raw.csv $P/${T}_ncu_k_aggregate_tc_asw.md $P/ncu_traffic.json > /dev/null
   else python tools/ncu_summary.py $O/$k.raw.csv $P/${T}_ncu_k_aggregate_ws_${k%_ws}.md > /dev/null; fi
   ncu -i $O/$k.ncu-rep --page source --csv > $O/$k.src.csv
-  python tools/ncu_regions.py $O/$k.src.csv > $P/${T}_ncu_k_aggregate_ws_${k%_ws}_regions.txt
+  if [ $k = asw_tc ]; then python tools/ncu_regions.py $O/$k.src.csv > $P/${T}_ncu_k_aggregate_tc_asw_regions.txt
+  else python tools/ncu_regions.py $O/$k.src.csv > $P/${T}_ncu_k_aggregate_ws_${k%_ws}_regions.txt; fi
 done
 cp $O/bench_n1.json $P/${T}_bench_n1.json
 cp $O/bench_reference_arm.json $P/${T}_bench_reference_arm.json
@@ -41,3 +42,5 @@ for n, (c, v) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
 open(sys.argv[2], "w").write("\n".join(out) + "\n")
 print("\n".join(out))
 PY
+
+for f in sanitizer_memcheck.txt sanitizer_racecheck.txt parity_report.json; do [ -f $O/$f ] && cp $O/$f $P/${T}_$f; done

@@ -12,17 +12,20 @@
 constexpr int ITERS = 1024;
 __global__ void k_pat(unsigned* out, int pat) {
     extern __shared__ __align__(128) unsigned char sm[];
-    for (int i = threadIdx.x; i < 40000; i += blockDim.x) reinterpret_cast<unsigned*>(sm)[i] = i;
+    for (int i = threadIdx.x; i < 47000; i += blockDim.x) reinterpret_cast<unsigned*>(sm)[i] = i;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) % 12;
     const int xl = lane >> 3, dl = lane & 7, wx = warp / 4, wd = warp % 4;
     const int dg = (8 * wd + dl + 2 * xl) % 32, xg = 4 * wx + xl;
-    unsigned base = (unsigned)__cvta_generic_to_shared(sm);
+    unsigned base = (unsigned)__cvta_generic_to_shared(sm) + (pat >= 5 ? 121504u : 0u);   // 5, 6: at the kernel's real offsets (W2 rows)
+    if (pat == 6) base -= 121504u - 52384u;                                              // 6: W1 operand offset
     unsigned addr; int width = 16, step = 896;
     switch (pat) {
         case 0: addr = base + 4 * (96 - 8 - 8 * xg + 4 * dg); break;
         case 1: addr = base + xg * 144; step = 16; break;
         case 2: addr = base + 8 * xg * 132 + 4 * dg; width = 4; step = 132; break;
+        case 5: addr = base + 4 * (96 - 8 - 8 * xg + 4 * dg); break;
+        case 6: addr = base + xg * 144; step = 16; break;
         case 3: addr = base + 8 * xg * 140 + 4 * dg; width = 4; step = 140; break;
         default: addr = base + 4 * (96 - 8 - 8 * xg + 4 * (8 * wd + dl)); break;
     }
@@ -42,11 +45,11 @@ __global__ void k_pat(unsigned* out, int pat) {
 int main() {
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0)); int sms = p.multiProcessorCount;
     unsigned* out; CK(cudaMalloc(&out, 4 * sms * 384));
-    CK(cudaFuncSetAttribute(k_pat, cudaFuncAttributeMaxDynamicSharedMemorySize, 160000));
-    for (int pat = 0; pat <= 4; pat++) {
+    CK(cudaFuncSetAttribute(k_pat, cudaFuncAttributeMaxDynamicSharedMemorySize, 190000));
+    for (int pat = 0; pat <= 6; pat++) {
         cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-        k_pat<<<sms, 384, 160000>>>(out, pat); CK(cudaDeviceSynchronize());
-        CK(cudaEventRecord(e0)); k_pat<<<sms, 384, 160000>>>(out, pat); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        k_pat<<<sms, 384, 190000>>>(out, pat); CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0)); k_pat<<<sms, 384, 190000>>>(out, pat); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         printf("pattern %d: %.2f cycles per warp-load per SM\n", pat, ms * 1e-3 * 1.965e9 / (12.0 * ITERS * 16));
     }

@@ -32,6 +32,7 @@ for vals in rows[2:]:
     if "k_aggregate" in name:
         traffic["k_aggregate_dram_bytes_per_launch"] = mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")
         traffic["k_aggregate_ms_under_ncu"] = float(d["gpu__time_duration.sum"][1])
+        traffic["source"] = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one " + name.split("(")[0].strip() + " launch at C2 on one GPU"
 open(sys.argv[2], "w").write("\n".join(out) + "\n")
 if len(sys.argv) > 3:
     json.dump(traffic, open(sys.argv[3], "w"), indent=1)
