@@ -34,9 +34,6 @@
 //   * one thread (producer 3, lane 0) issues the 30 tcgen05.mma per window row and commits them onto the "weight stage
 //     free" mbarrier, whose count is consumers + 1.
 
-#ifndef SS_TC_MMA_DEFER
-#define SS_TC_MMA_DEFER 1      // 1: a row's MMAs are issued two at a time between the NEXT row's weight batches; 0: in one burst
-#endif
 #ifndef SS_TC_CREG
 #define SS_TC_CREG 136         // registers per consumer / producer thread after setmaxnreg: 12 * CREG + 4 * PREG = 16 * 128
 #define SS_TC_PREG 96
@@ -221,48 +218,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
         const int o_f1 = sp.f1, o_f2 = sp.f2, o_pa = sp.pa, o_w1 = sp.w1, o_w2 = sp.w2;
         const int b_f1 = sp.f1bytes, b_f2 = sp.f2bytes, b_pa = sp.pabytes, b_w2 = sp.w2bytes, w1arr = sp.w1arr;
 
-        // ---- the tensor core: D[r][x] += W2hi*W1hi + W2hi*W1lo + W2lo*W1hi per window row, issued by lane 0 of producer 3 ----
-        // (Measured on the B200: without the MMAs the kernel is 9 % faster, SS_FREERUN=8 -- issued in one burst, a row's 30 MMAs
-        // hold the issuing scheduler for about as long as they run.  Splitting the burst over two producers, one accumulator
-        // half each, measured 2 % SLOWER; a 17th warp for it cannot get registers, see TC_THREADS.)  With double-staged operands
-        // the MMAs of row n are therefore DEFERRED: they are issued two at a time between producer 3's weight batches of row
-        // n + 1, so the tensor pipe never backs up into the issue slot.  Each accumulator half is still fed in program order by
-        // one thread: bit-reproducible.
-        constexpr bool DEFER = SS_TC_MMA_DEFER && !SINGLE;
         constexpr int PUNROLL = SS_TC_PUNROLL;
-        const int MM = 6 * KG;                                   // MMAs per window row: 2 halves x 3 terms x KG
-        int mm_row = -1, mm_done = 0, mm_stage = 0;              // pending row (producer 3; uniform across the warp)
-        auto mma_one = [&](int row, int stage, int m) {          // lane 0 only
-            const int half = m / (3 * KG), t = m - half * 3 * KG, term = t / KG, kg = t - term * KG;
-            const uint32_t bhi = smem_u32(smem + sp.w1 + stage * sp.w1arr);
-            const uint32_t blo = smem_u32(smem + sp.w1 + (2 + (SINGLE ? 0 : stage)) * sp.w1arr);
-            const uint32_t a0 = tbase + colA(stage, half, term == 2);
-            const u64 bd = tc_sdesc((term == 1 ? blo : bhi) + (uint32_t)kg * TC_KGB, TC_LBO, TC_SBO);
-            const uint32_t acc = !(row == 0 && term == 0 && kg == 0);
-            if (!(P.freerun & 8))                                // timing experiment: no MMAs (the commits still arrive)
-                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tbase + 96u * half),
-                             "r"(a0 + 8u * kg), "l"(bd), "r"(tc_idesc(128, T)), "r"(acc)
-                             : "memory");
-        };
-        auto mma_pump = [&](int k) {                             // issue up to k MMAs of the pending row; commit after the last
-            if (mm_row < 0) return;
-            const int upto = min(MM, mm_done + k);
-            if (lane == 0) {
-                for (int m = mm_done; m < upto; ++m) mma_one(mm_row, mm_stage, m);
-                if (upto == MM) {
-                    // completion of everything issued so far arrives on "weight stage free" (and on barrier 7 when the
-                    // operands are single-staged)
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(8 + mm_stage)) : "memory");
-                    if (SINGLE)
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(BAR(7)) : "memory");
-                }
-            }
-            __syncwarp();
-            mm_done = upto;
-            if (upto == MM) mm_row = -1;
-        };
-
         int sw = 0, phw = 0;
         for (int n = 0; n < nsteps; ++n) {
             const int st = n & 1, ph = (n >> 1) & 1;
@@ -279,10 +235,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
             mbar_wait(BAR(1 + st), ph);            // features of this window row have landed
             mbar_wait(BAR(8 + sw), phw ^ 1);  // consumers AND the tensor core are done with this weight stage
             if (SINGLE && n > 0) mbar_wait(BAR(7), (n - 1) & 1);   // single-stage operands: the previous row's MMAs have read them
-            if (DEFER && pw == 3 && n > 0) {
-                mbar_wait(BAR(5 + (sw ^ 1)), sw == 0 ? phw ^ 1 : phw);   // every producer has finished the previous row
-                mm_row = n - 1; mm_done = 0; mm_stage = sw ^ 1;
-            }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
             const float4 *f1 = reinterpret_cast<const float4 *>(smem + o_f1 + st * b_f1);
@@ -321,7 +273,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
                            __float_as_uint(tc_lo(w3)));
                     nb += 4;
                     dst += 4 * NRp;
-                    if (DEFER && pw == 3) mma_pump(2);
                 }
             }
             // ---- left columns: K-major operand shared by the consumers and the tensor core (hi) + its residual (lo) ----
@@ -346,9 +297,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
                 *reinterpret_cast<float4 *>(W1hi + qo) = make_float4(w0, w1, w2, w3);
                 *reinterpret_cast<float4 *>(W1lo + qo) = make_float4(tc_lo(w0), tc_lo(w1), tc_lo(w2), tc_lo(w3));
                 if (++jb == NB) { jb = 0; ++blk; }
-                if (DEFER && pw == 3) mma_pump(2);
             }
-            if (DEFER && pw == 3) mma_pump(MM);                      // whatever is left of the previous row
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> tensor-core (async proxy) reads
@@ -358,23 +307,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
                 mbar_arrive(BAR(3 + st));        // feature stage may be refilled
             }
             // ---- the tensor core: D[r][x] += W2hi*W1hi + W2hi*W1lo + W2lo*W1hi over this window row ----
-            if (pw == 3 && !DEFER) {                                 // burst: this row's MMAs right away
+            // ---- the tensor core: D[r][x] += W2hi*W1hi + W2hi*W1lo + W2lo*W1hi over this window row ----
+            // Producer 3 issues the row's 6 KG MMAs (30 for a 35-wide window).  The whole warp runs the loop in convergent flow
+            // and the instruction itself is predicated on elect.sync, so every operand lives in uniform registers: about 10
+            // uniform instructions per MMA.  Issued from an `if (lane == 0)` branch ptxas wraps each tcgen05.mma in an ELECT /
+            // R2UR.BROADCAST / BRA.U.ANY loop, 22-25 instructions per MMA, on a warp that only gets an issue slot every few
+            // cycles -- that, not the tensor pipe, was most of what the MMAs cost (without them the kernel is 9 % faster,
+            // SS_FREERUN=8).  Tried and rejected: the issue split over two producers (-2 %), issued two at a time
+            // between the next row's weight batches (the bookkeeping costs more than it hides), a 17th warp (see TC_THREADS).
+            if (pw == 3) {
                 mbar_wait(BAR(5 + sw), phw);     // every producer has arrived: the operands of this row are in place
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                mm_row = n; mm_done = 0; mm_stage = sw;
-                mma_pump(MM);
+                const int KGx = (P.freerun & 8) ? 0 : KG;         // timing experiment: no MMAs (the commits still arrive)
+                // (shuffles from lane 0: ptxas then knows these are warp-uniform)
+                const uint32_t bhi = __shfl_sync(0xffffffffu, smem_u32(smem) + (uint32_t)(o_w1 + sw * w1arr), 0);
+                const uint32_t blo = __shfl_sync(0xffffffffu, smem_u32(smem) + (uint32_t)(o_w1 + (2 + (SINGLE ? 0 : sw)) * w1arr), 0);
+                const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0), ca = __shfl_sync(0xffffffffu, colA(sw, 0, 0), 0);
+                const int KGu = __shfl_sync(0xffffffffu, KGx, 0), first = __shfl_sync(0xffffffffu, n == 0 ? 1 : 0, 0);
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {
+                        uint32_t a = tb + ca + (uint32_t)half * (SINGLE ? 2u * KC : 80u) + (term == 2 ? (SINGLE ? KC : 40u) : 0u);
+                        u64 bd = tc_sdesc(term == 1 ? blo : bhi, TC_LBO, TC_SBO);
+#pragma unroll 1
+                        for (int kg = 0; kg < KGu; ++kg) {
+                            const uint32_t acc = !(first && term == 0 && kg == 0);
+                            asm volatile("{\n.reg .pred p, pe;\nsetp.ne.b32 p, %4, 0;\nelect.sync _|pe, 0xffffffff;\n"
+                                         "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tb + 96u * half),
+                                         "r"(a), "l"(bd), "r"(tc_idesc(128, T)), "r"(acc)
+                                         : "memory");
+                            a += 8u;
+                            bd += (u64)(TC_KGB >> 4);
+                        }
+                    }
+                }
+                // completion of everything issued so far arrives on "weight stage free" (and on barrier 7 when the operands are
+                // single-staged)
+                asm volatile("{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
+                             "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(BAR(8 + sw)) : "memory");
+                if (SINGLE)
+                    asm volatile("{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
+                                 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(BAR(7)) : "memory");
             }
             if (++sw == 2) { sw = 0; phw ^= 1; }
         }
         // ---- denominators: TMEM -> shared memory [r][x] once the last window row is fully consumed and accumulated ----
         {
             const int swl = sw ^ 1, phl = sw == 0 ? phw ^ 1 : phw;   // stage / phase of the last window row
-            if (DEFER && pw == 3) {                                  // its MMAs are still to be issued
-                mbar_wait(BAR(5 + swl), phl);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                mm_row = nsteps - 1; mm_done = 0; mm_stage = swl;
-                mma_pump(MM);
-            }
+
             mbar_wait(BAR(8 + swl), phl);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float *Ds = reinterpret_cast<float *>(smem + sp.ds);
