@@ -419,6 +419,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
             const unsigned char *w1q = smem + (sp.w1 + sw * sp.w1arr) + xg * TC_SBO;
             const float *w2p = reinterpret_cast<const float *>(smem + (sp.w2 + sw * sp.w2bytes)) + R0;
             float4 wq[8];
+#ifdef SS_DEBUG_ADDR
+            // shared-memory byte addresses of this lane's three load streams (first window row of one interior block)
+            if (n == 0 && blockIdx.x == 5)
+                printf("ADDR %d %d %u %u %u\n", warp, lane, smem_u32(w2p), smem_u32(w1q), smem_u32(ep));
+#endif
 
             auto step = [&](auto sc) {
                 constexpr int s = decltype(sc)::value;
