@@ -175,8 +175,8 @@ int ss_gsw_stages(const uint8_t *img1, const uint8_t *img2, int width, int heigh
  * ColorConversion::ImageFromBGR2Lab (headers/colorconversion.hpp:18-86) on its own, for parity tests. */
 int ss_debug_lab(const uint8_t *img, int width, int height, float *out_lab);
 
-/* Which aggregation kernel served the last call on `device` (< 0: the device of the host entry points): 1 = k_aggregate_tc,
- * 3 = k_aggregate_tc8 (both: tensor-core denominators), 2 = k_aggregate_ws (all CUDA cores), 0 = none yet; *disp_chunk (may be NULL) receives the
+/* Which aggregation kernel served the last call on `device` (< 0: the device of the host entry points): 1 = k_aggregate_tc
+ * (tensor-core denominators), 2 = k_aggregate_ws (all CUDA cores), 0 = none yet; *disp_chunk (may be NULL) receives the
  * disparity chunk it ran with.  Lets the parity tests assert that a case reached the kernel it is meant to cover. */
 int ss_debug_last_kernel(int device, int *disp_chunk);
 

@@ -154,13 +154,13 @@ def last_kernel(device=-1):
     """("tc" | "ws" | None, disparity chunk) of the last aggregation launch on ``device``."""
     dc = ctypes.c_int()
     k = lib().ss_debug_last_kernel(device, ctypes.byref(dc))
-    return {1: "tc", 2: "ws", 3: "tc"}.get(k), dc.value
+    return {1: "tc", 2: "ws"}.get(k), dc.value
 
 
 def last_kernel_name(device=-1):
-    """"k_aggregate_tc8" | "k_aggregate_tc" | "k_aggregate_ws" | None of the last aggregation launch on ``device``."""
+    """"k_aggregate_tc" | "k_aggregate_ws" | None of the last aggregation launch on ``device``."""
     k = lib().ss_debug_last_kernel(device, None)
-    return {1: "k_aggregate_tc", 2: "k_aggregate_ws", 3: "k_aggregate_tc8"}.get(k)
+    return {1: "k_aggregate_tc", 2: "k_aggregate_ws"}.get(k)
 
 
 def lab(img):

@@ -307,14 +307,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
                 mbar_arrive(BAR(3 + st));        // feature stage may be refilled
             }
             // ---- the tensor core: D[r][x] += W2hi*W1hi + W2hi*W1lo + W2lo*W1hi over this window row ----
-            // ---- the tensor core: D[r][x] += W2hi*W1hi + W2hi*W1lo + W2lo*W1hi over this window row ----
-            // Producer 3 issues the row's 6 KG MMAs (30 for a 35-wide window).  The whole warp runs the loop in convergent flow
-            // and the instruction itself is predicated on elect.sync, so every operand lives in uniform registers: about 10
-            // uniform instructions per MMA.  Issued from an `if (lane == 0)` branch ptxas wraps each tcgen05.mma in an ELECT /
-            // R2UR.BROADCAST / BRA.U.ANY loop, 22-25 instructions per MMA, on a warp that only gets an issue slot every few
-            // cycles -- that, not the tensor pipe, was most of what the MMAs cost (without them the kernel is 9 % faster,
-            // SS_FREERUN=8).  Tried and rejected: the issue split over two producers (-2 %), issued two at a time
-            // between the next row's weight batches (the bookkeeping costs more than it hides), a 17th warp (see TC_THREADS).
+            // Producer 3 issues the row's 6 KG MMAs (30 for a 35-wide window): the whole warp runs the loop, the instruction
+            // itself is predicated on elect.sync.  The issue is NOT free: without the MMAs the kernel is 6 % faster (SS_FREERUN=8)
+            // -- about 18 instructions per MMA on a warp that only gets an issue slot every few cycles and whose weights the
+            // whole block waits for.  Tried and rejected: the issue split over two producers (+2 %), issued two at
+            // a time between the next row's weight batches (the bookkeeping costs more than it hides), a 17th warp (see
+            // TC_THREADS).
             if (pw == 3) {
                 mbar_wait(BAR(5 + sw), phw);     // every producer has arrived: the operands of this row are in place
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

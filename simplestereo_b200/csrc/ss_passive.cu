@@ -797,7 +797,6 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
 }
 
 #include "ss_aggregate_tc.cuh"
-#include "ss_aggregate_tc8.cuh"
 
 __global__ void k_merge_keys(u64 *__restrict__ keys, int nshards, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -959,7 +958,6 @@ struct Ctx {
     int last_dc = 0;                 // and its disparity chunk
     int smem_attr_ws[24] = {};       // largest dynamic-smem opt-in set so far, per k_aggregate_ws instantiation
     int smem_attr_tc[8] = {};        // same for k_aggregate_tc
-    int smem_attr_tc8[4] = {};       // same for k_aggregate_tc8
 };
 
 constexpr int SS_MAX_DEVICES = 64;
@@ -1024,7 +1022,6 @@ void ctx_release(Ctx &c) {
     c.ready = false;
     memset(c.smem_attr_ws, 0, sizeof(c.smem_attr_ws));
     memset(c.smem_attr_tc, 0, sizeof(c.smem_attr_tc));
-    memset(c.smem_attr_tc8, 0, sizeof(c.smem_attr_tc8));
 }
 
 // c.mu held.  Leaves `device` current.
@@ -1136,17 +1133,11 @@ bool tc_enabled() {             // SS_TCDEN=0 forces the all-CUDA-core kernel (r
     return !(e && atoi(e) == 0);
 }
 
-bool tc8_enabled() {            // SS_TC8=0 keeps the 96-column kernel (A/B timing, and the tests compare the two)
-    const char *e = getenv("SS_TC8");
-    return !(e && atoi(e) == 0);
-}
-
 // The kernel family and the disparity chunk DC are chosen from the CALL's range [minD, maxD], never from the evaluated
 // sub-range: a disparity shard (ss_asw_partial_device) runs the same kernel on the same chunk grid -- chunks start at
 // minD + k * DC -- as the unsharded call, so its costs are bit-identical and merged shards reproduce the unsharded map.
 struct Plan {
-    bool tc;     // tensor-core denominators (ASW, 128-disparity chunks, win <= TC_MAX_WIN); else k_aggregate_ws
-    bool tc8;    // ... with the 128-column / 8 x 8 lane-tile kernel k_aggregate_tc8 (win <= 35); else k_aggregate_tc
+    bool tc;     // k_aggregate_tc (ASW, 128-disparity chunks, win <= TC_MAX_WIN); else k_aggregate_ws
     int DC;      // 0: nothing fits
 };
 Plan make_plan(const Call &q) {
@@ -1154,7 +1145,6 @@ Plan make_plan(const Call &q) {
     Plan p;
     p.DC = D <= 32 ? 32 : (D <= 64 ? 64 : 128);
     p.tc = !q.gsw && p.DC == 128 && q.win <= TC_MAX_WIN && tc_enabled() && tc_smem(q.win, q.win > 39).total <= 227 * 1024;
-    p.tc8 = p.tc && q.win <= 35 && tc8_smem(q.win).total <= 227 * 1024 && tc8_enabled();
     if (!p.tc) {
         // windows whose tiles do not fit at this chunk size run narrower chunks (several chunks merge through the atomicMin keys)
         while (p.DC > 32 && !ws_fits(q.win, p.DC, q.gsw)) p.DC /= 2;
@@ -1163,7 +1153,7 @@ Plan make_plan(const Call &q) {
     return p;
 }
 
-Geom make_geom(const Call &q, int DC, bool tc8 = false) {
+Geom make_geom(const Call &q, int DC) {
     Geom g;
     g.W = q.W; g.H = q.H; g.win = q.win; g.pad = q.win / 2;
     g.minD = q.minD; g.maxD = q.maxD;
@@ -1176,8 +1166,8 @@ Geom make_geom(const Call &q, int DC, bool tc8 = false) {
     g.row0 = q.row0; g.row1 = q.row1;
     g.erow0 = q.row0 - g.pad < 0 ? 0 : q.row0 - g.pad;
     g.erow1 = q.row1 + g.pad > q.H ? q.H : q.row1 + g.pad;
-    g.T = q.gsw ? TILE_X : (tc8 ? TC8_T : TILE_WS);
-    g.EP = tc8 ? TC8_EP : g.DC + 4;
+    g.T = q.gsw ? TILE_X : TILE_WS;
+    g.EP = g.DC + 4;
     g.ntx = (q.W + g.T - 1) / g.T;
     g.UW = (g.ntx * g.T + g.win - 1 + 3) & ~3;
     g.PL2 = g.dLo + g.nch * g.DC - 1 + g.pad;
@@ -1277,20 +1267,6 @@ int launch_tc_s(Ctx &c, const AggParams &P, cudaStream_t st) {
 int launch_tc(Ctx &c, const AggParams &P, cudaStream_t st) {
     return P.g.win <= 39 ? launch_tc_s<false>(c, P, st) : launch_tc_s<true>(c, P, st);
 }
-template <int REM>
-int launch_tc8_rem(Ctx &c, const AggParams &P, cudaStream_t st) {
-    c.blocks_per_sm = 1;
-    return launch_agg(c, k_aggregate_tc8<REM>, c.smem_attr_tc8[REM / 2], tc8_smem(P.g.win).total, P, TC8_THREADS, st);
-}
-int launch_tc8(Ctx &c, const AggParams &P, cudaStream_t st) {
-    switch (P.g.win & 7) {
-        case 1: return launch_tc8_rem<1>(c, P, st);
-        case 3: return launch_tc8_rem<3>(c, P, st);
-        case 5: return launch_tc8_rem<5>(c, P, st);
-        default: return launch_tc8_rem<7>(c, P, st);
-    }
-}
-
 struct Outputs {
     int16_t *d_final = nullptr;     // [(rows)*W]
     int16_t *d_left = nullptr, *d_right = nullptr;
@@ -1341,7 +1317,7 @@ int run_device(Ctx &c, const Call &q, const uint8_t *d_img1, const uint8_t *d_im
         Call qq = q;
         qq.dBegin = dB;
         qq.dEnd = dE;
-        const Geom g = make_geom(qq, plan.DC, plan.tc8);
+        const Geom g = make_geom(qq, plan.DC);
         const int erows = g.erow1 - g.erow0;
         if ((rc = ensure(c.f1, (size_t)erows * g.UW * 16))) return rc;
         if ((rc = ensure(c.f2, (size_t)erows * g.VW * 16))) return rc;
@@ -1413,11 +1389,10 @@ int run_device(Ctx &c, const Call &q, const uint8_t *d_img1, const uint8_t *d_im
         P.dbg = g_dbg;
 #endif
         if (q.gsw) rc = launch_ws<true>(c, P, st);
-        else if (plan.tc8) rc = launch_tc8(c, P, st);
         else if (plan.tc) rc = launch_tc(c, P, st);
         else rc = launch_ws<false>(c, P, st);
         if (rc) return rc;
-        c.last_kernel = (!q.gsw && plan.tc8) ? 3 : (!q.gsw && plan.tc) ? 1 : 2;
+        c.last_kernel = (!q.gsw && plan.tc) ? 1 : 2;
         c.last_dc = g.DC;
     }
     if (!partial) {

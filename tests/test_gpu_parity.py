@@ -558,18 +558,16 @@ def test_c_abi_from_plain_c(tmp_path):
 
 
 def test_tensor_core_and_cuda_core_aggregation_agree(monkeypatch):
-    """ASW with 128-disparity chunks runs the tensor-core denominators (tcgen05, 3xTF32 + centred truncation bound):
-    k_aggregate_tc8 (128-column tiles, 8 x 8 lane tiles; win <= 35) or k_aggregate_tc (96-column tiles; SS_TC8=0, and win 37-41,
-    where 41 is its single-staged operand variant); SS_TCDEN=0 forces the all-CUDA-core k_aggregate_ws.  Same parity bar for all
-    three, and they must agree with each other: costs to 5e-5, maps except at near-ties."""
+    """ASW with 128-disparity chunks runs k_aggregate_tc (denominators on tcgen05, 3xTF32 + centred truncation bound; win 41 is
+    its single-staged operand variant); SS_TCDEN=0 forces the all-CUDA-core k_aggregate_ws.  Same parity bar for both, and
+    they must agree with each other: costs to 5e-5, maps except at near-ties."""
     from simplestereo_b200 import _cabi
     l, r, _ = synth_pair(330, 44, 139, 17)
     for win in (35, 39, 41):
         kw = dict(winSize=win, maxDisparity=139, minDisparity=0, gammaC=9.0, gammaP=25.0, consistent=True)
         ref = oracle.asw(l, r, stages=True, cost=True, **kw)
         out = {}
-        for name, env, want in (("tc8", {}, "k_aggregate_tc8" if win <= 35 else "k_aggregate_tc"),
-                                ("tc", {"SS_TC8": "0"}, "k_aggregate_tc"), ("ws", {"SS_TCDEN": "0"}, "k_aggregate_ws")):
+        for name, env, want in (("tc", {}, "k_aggregate_tc"), ("ws", {"SS_TCDEN": "0"}, "k_aggregate_ws")):
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             out[name] = ss.passive.StereoASW(**kw).compute_staged(l, r, cost=True)
@@ -579,8 +577,7 @@ def test_tensor_core_and_cuda_core_aggregation_agree(monkeypatch):
             parity.check_cost(out[name]["cost"], ref["cost"])
             parity.check_staged(out[name], ref, ref["cost"], ref["cost"], 0, True, max_fraction=0.01)
         fin = np.isfinite(out["ws"]["cost"])
-        for name in ("tc8", "tc"):
-            assert np.array_equal(fin, np.isfinite(out[name]["cost"]))
-            assert np.allclose(out[name]["cost"][fin], out["ws"]["cost"][fin], rtol=5e-5, atol=1e-5)
-            # where the two maps differ, the two picks are a near-tie of the oracle's own costs
-            parity.adjudicate_left(out[name]["left"], out["ws"]["left"], ref["cost"], 0, max_fraction=None)
+        assert np.array_equal(fin, np.isfinite(out["tc"]["cost"]))
+        assert np.allclose(out["tc"]["cost"][fin], out["ws"]["cost"][fin], rtol=5e-5, atol=1e-5)
+        # where the two maps differ, the two picks are a near-tie of the oracle's own costs
+        parity.adjudicate_left(out["tc"]["left"], out["ws"]["left"], ref["cost"], 0, max_fraction=None)
