@@ -286,9 +286,6 @@ struct AggParams {
     int Dp;               // pitch of vol0/vol1 (= nch*DC)
     int vol_export;       // the volumes are returned to the caller (debug export): unevaluated pairs must read +inf
     int freerun;          // timing experiments (SS_FREERUN bit mask, see run_device); results are garbage
-#ifdef SS_DEBUG_DUMP
-    float *dbg;           // [0]=bx [1]=by [2]=step ; dump of W1s, W2s, Es of that block/step follows at dbg+16
-#endif
 };
 
 template <bool GSW>
@@ -965,9 +962,6 @@ Ctx g_ctxs[SS_MAX_DEVICES];
 std::mutex g_cfg_mu;
 std::vector<int> g_devices;          // devices the host entry points run on (ss_init / ss_init_devices); empty: current device
 bool g_profile = false;
-#ifdef SS_DEBUG_DUMP
-float *g_dbg = nullptr;
-#endif
 
 int fail(int code, const std::string &msg) {
     t_err = msg;
@@ -1385,9 +1379,6 @@ int run_device(Ctx &c, const Call &q, const uint8_t *d_img1, const uint8_t *d_im
             const char *e = getenv("SS_FREERUN");
             P.freerun = e ? atoi(e) : 0;
         }
-#ifdef SS_DEBUG_DUMP
-        P.dbg = g_dbg;
-#endif
         if (q.gsw) rc = launch_ws<true>(c, P, st);
         else if (plan.tc) rc = launch_tc(c, P, st);
         else rc = launch_ws<false>(c, P, st);
@@ -1943,19 +1934,6 @@ int ss_measure_fp32_peak(double *tflops, void *stream) {
     return scratch_end(c, st);
 }
 
-#ifdef SS_DEBUG_DUMP
-int ss_debug_set(int bx, int by, int step, int nfloats) {
-    if (!g_dbg) cudaMalloc(&g_dbg, (size_t)(nfloats + 16) * 4);
-    float h[3] = {(float)bx, (float)by, (float)step};
-    cudaMemcpy(g_dbg, h, sizeof(h), cudaMemcpyHostToDevice);
-    return 0;
-}
-int ss_debug_get(float *out, int nfloats) {
-    cudaDeviceSynchronize();
-    cudaMemcpy(out, g_dbg + 16, (size_t)nfloats * 4, cudaMemcpyDeviceToHost);
-    return 0;
-}
-#endif
 
 }  // extern "C"
 

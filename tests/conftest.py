@@ -41,5 +41,12 @@ def pytest_sessionfinish(session, exitstatus):
     import json
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
-    with open(os.path.join(out, "parity_report.json"), "w") as f:
-        json.dump(parity.REPORT, f, indent=1, sort_keys=True)
+    path = os.path.join(out, "parity_report.json")
+    merged = {}
+    try:                                   # several pytest sessions of one GPU call (full suite, sanitizer subsets) add up
+        merged = json.load(open(path))
+    except Exception:
+        pass
+    merged.update(parity.REPORT)
+    with open(path, "w") as f:
+        json.dump(merged, f, indent=1, sort_keys=True)
