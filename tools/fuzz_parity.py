@@ -2,7 +2,7 @@
 
     python tools/fuzz_parity.py [n_cases] [seed]
 
-Shapes 1..260 x 1..48, windows 1..51, disparity ranges up to 300 (multi-chunk), minDisparity up to 9, both matchers,
+Shapes 1..260 x 1..48 (a fifth of the cases up to 400 x 160: several waves of blocks, tail-wave split), windows 1..51, disparity ranges up to 300 (multi-chunk), minDisparity up to 9, both matchers,
 consistent on/off.  Every case goes through parity.check_cost + parity.check_staged.
 """
 import os
@@ -26,6 +26,10 @@ for case in range(n):
     w, h = int(rng.integers(1, 261)), int(rng.integers(1, 49))
     mind = int(rng.integers(0, 10)) if rng.random() < 0.4 else 0
     maxd = mind + int(rng.choice([0, 3, 15, 31, 32, 63, 64, 100, 127, 128, 200, 300]))
+    tall = rng.random() < 0.2                               # enough tiles for more than one wave of 148 blocks: the tail-wave split
+    if tall:
+        w, h = int(rng.integers(97, 400)), int(rng.integers(49, 161))
+        maxd = mind + int(rng.choice([70, 100, 127, 128, 200]))
     kind = rng.random()
     pair_seed = int(rng.integers(0, 1 << 30))
     if kind < 0.75:
@@ -41,7 +45,7 @@ for case in range(n):
     desc = None
     try:
         if rng.random() < 0.6:
-            kw = dict(winSize=int(rng.choice([1, 3, 5, 9, 15, 21, 33, 35, 37, 51])), maxDisparity=maxd, minDisparity=mind,
+            kw = dict(winSize=int(rng.choice([1, 3, 5, 9, 15, 21] if tall else [1, 3, 5, 9, 15, 21, 33, 35, 37, 41, 51])), maxDisparity=maxd, minDisparity=mind,
                       gammaC=float(rng.uniform(2, 25)), gammaP=float(rng.uniform(4, 40)), consistent=bool(rng.integers(0, 2)))
             desc = ("asw", w, h, kw)
             gpu = ss.passive.StereoASW(**kw).compute_staged(l, r, cost=True)
@@ -50,7 +54,7 @@ for case in range(n):
             nl, nr = parity.check_staged(gpu, ref, ref["cost"], ref["cost"], mind, kw["consistent"],
                                          None if stress else 0.02)
         else:
-            kw = dict(winSize=int(rng.choice([1, 3, 5, 7, 9, 11, 15, 21, 35, 51])), maxDisparity=maxd, minDisparity=mind,
+            kw = dict(winSize=int(rng.choice([1, 3, 5, 7, 9, 11] if tall else [1, 3, 5, 7, 9, 11, 15, 21, 35, 51])), maxDisparity=maxd, minDisparity=mind,
                       gamma=int(rng.integers(2, 30)), fMax=float(rng.uniform(20, 300)), iterations=int(rng.integers(0, 4)), bins=20)
             desc = ("gsw", w, h, kw)
             gpu = ss.passive.StereoGSW(**kw).compute_staged(l, r, cost=True)
