@@ -46,6 +46,11 @@ constexpr int TC_SBO = 144;                       // bytes between 8-column grou
 constexpr int TC_LBO = (TILE_WS / 8) * TC_SBO;    // bytes between the two 4-offset chunks of a K group
 constexpr int TC_KGB = 2 * TC_LBO;                // bytes per K group (8 window offsets)
 constexpr int TC_DS_BYTES = 224 * TILE_WS * 4;    // denominators read back: [r][x]
+// Raw-cost tile: 128 bytes per column (4 disparities per word, 32 words = one pass over the banks) plus 24 bytes after every
+// 8 columns.  A consumer lane reads the word of (column 8 xg + a, disparity group dg), dg = dl + 2 xl rotated: its bank is
+// 6 xg + dg = 8 xl + dl (+ a warp constant), 32 distinct banks -- one wavefront per load.  (Round 2 measured two with the
+// uniform 132-byte pitch: 10 xl + dl collides for xl = 0 / 3.)
+constexpr int TC_EP = 128, TC_EG = 24;
 constexpr float TC_TRUNC_PER_MMA = 5.9604645e-8f;  // 2^-24: half the worst-case relative truncation loss of one tcgen05.mma
 
 struct TcSmem {
@@ -54,10 +59,10 @@ struct TcSmem {
 };
 // left-weight operand region: [hi stage 0 | hi stage 1 | lo stage 0 | lo stage 1 (absent when single)]
 __host__ __device__ inline TcSmem tc_smem(int win, bool single) {
-    const int T = TILE_WS, DC = 128, NU = T + win - 1, NR = T + DC - 1, NRp = T + DC, NV = NR + win - 1, EP = DC + 4;
+    const int T = TILE_WS, DC = 128, NU = T + win - 1, NR = T + DC - 1, NRp = T + DC, NV = NR + win - 1;
     const int winq = (win + 3) >> 2, winr = winq * 4, KG = (win + 7) >> 3;
     TcSmem p;
-    p.ebytes = (NU * EP + 15) & ~15;
+    p.ebytes = (NU * TC_EP + ((NU + 7) >> 3) * TC_EG + 15) & ~15;   // tiles start at a multiple of 8 columns
     p.f1bytes = NU * 16;
     p.f2bytes = NV * 16;
     p.pabytes = winq * 16;
@@ -97,7 +102,7 @@ constexpr int TC_THREADS = 512;
 
 template <int REM, bool SINGLE>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams P) {
-    constexpr int DC = 128, T = TILE_WS, NRp = T + DC, EP = DC + 4, CW = 12, PW = 4, NDB = 4, NT = TC_THREADS;
+    constexpr int DC = 128, T = TILE_WS, NRp = T + DC, EP = TC_EP, EG = TC_EG, CW = 12, PW = 4, NDB = 4, NT = TC_THREADS;
     extern __shared__ __align__(128) unsigned char smem[];
 
     const Geom &g = P.g;
@@ -170,7 +175,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
         const uint32_t lane_base = (uint32_t)(pw * 32) << 16;       // this warp's quarter of the TMEM lanes
         const int f2_start = x0 - dlo - DC + 1 - pad + g.PL2;
         const int c2_start = x0 - dlo - DC + 1 + g.PL2;
-        const size_t e_plane = (size_t)g.UW * EP;
+        const size_t e_plane = (size_t)g.EPL;
         const float4 *C1s = reinterpret_cast<const float4 *>(smem + sp.c1);
         const float4 *C2s = reinterpret_cast<const float4 *>(smem + sp.c2);
 
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
             const uint32_t bar = BAR(11 + st);
             mbar_expect_tx(bar, (uint32_t)sp.ebytes);
             tma_load_1d(smem_u32(smem + (sp.e + st * sp.ebytes)),
-                        static_cast<const uint8_t *>(P.E) + ((size_t)ch * erows + (ii - g.erow0)) * e_plane + (size_t)x0 * EP,
+                        static_cast<const uint8_t *>(P.E) + ((size_t)ch * erows + (ii - g.erow0)) * e_plane + (size_t)x0 * EP + (size_t)(x0 >> 3) * EG,
                         (uint32_t)sp.ebytes, bar);
         };
         if (pw == 0 && lane == 0) {
@@ -404,7 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
         mbar_wait(BAR(11 + st), ph);             // raw costs of this window row
         if (warp_live && !(P.freerun & 4)) {
             u64 ring[8][2];
-            const uint8_t *ep = smem + (sp.e + st * sp.ebytes) + xb * EP + kb;
+            const uint8_t *ep = smem + (sp.e + st * sp.ebytes) + xb * EP + xg * EG + kb;
             auto load_e = [&](const uint8_t *q, u64 &lo, u64 &hi) {
                 const uint32_t e = *reinterpret_cast<const uint32_t *>(q);
                 lo = pk(u8_to_f32(e, 0), u8_to_f32(e, 1));
@@ -425,7 +430,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
 
             auto step = [&](auto sc) {
                 constexpr int s = decltype(sc)::value;
-                load_e(ep + s * EP, ring[(7 + s) & 7][0], ring[(7 + s) & 7][1]);
+                load_e(ep + s * EP + (s > 0 ? EG : 0), ring[(7 + s) & 7][0], ring[(7 + s) & 7][1]);   // column xb + 7 + s: next group
                 if (s % 4 == 0) {
 #pragma unroll
                     for (int a = 0; a < 8; ++a) wq[a] = *reinterpret_cast<const float4 *>(w1q + (s / 4) * TC_LBO + a * 16);
@@ -452,7 +457,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
             auto period = [&]() {
                 step(IC<0>{}); step(IC<1>{}); step(IC<2>{}); step(IC<3>{});
                 step(IC<4>{}); step(IC<5>{}); step(IC<6>{}); step(IC<7>{});
-                ep += 8 * EP;
+                ep += 8 * EP + EG;
                 w1q += TC_KGB;
                 w2p += 8 * NRp;
             };

@@ -163,7 +163,10 @@ struct Geom {
     int nsub;          // 1, or T/32 for the launch that covers the last partial wave: blockIdx.y then restricts a block
                        // to ONE 32-column block of its tile (same arithmetic per pair, a third of the work per SM)
     int T;             // output columns per block: 64 (GSW) or 96 (ASW)
-    int EP;            // ASW: bytes per cost-volume column (DC + 4: the +4 skews columns 8 apart onto different banks)
+    int EP, EG;        // ASW raw-cost plane: column c of a row starts at byte c * EP + (c >> 3) * EG.  k_aggregate_ws: EP = DC + 4,
+                       // EG = 0; k_aggregate_tc: EP = 128, EG = 24 -- lane groups 8 columns apart then start 6 banks apart, which
+                       // with the consumers' disparity-group rotation (2 per group) spreads a warp's 32 words over 32 banks
+    int EPL;           // bytes per (chunk, row) plane of the ASW raw-cost volume (multiple of 16: TMA source alignment)
     int ntx;           // number of T-column tiles
     int UW;            // padded row pitch of the left feature image and of the cost volume (u' = u + pad)
     int VW, PL2;       // padded row pitch / left padding of the right feature image (xr' = xr + PL2)
@@ -261,7 +264,8 @@ __global__ void k_cost_volume(const uint8_t *__restrict__ img1, const uint8_t *_
     } else {
         // ASW: the truncated AD is an integer in [0,40] -> one byte; 4 disparities per 32-bit word.  (A bfloat16 tile -- exact
         // for these integers, byte permutes instead of I2F.U8 in the consumers -- measured 0.5 % slower at C2.)
-        *reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(Eout) + col * g.EP + kq) =
+        *reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(Eout) + ((size_t)ch * (g.erow1 - g.erow0) + r) * g.EPL + (size_t)up * g.EP +
+                                      (size_t)(up >> 3) * g.EG + kq) =
             (uint32_t)vi[0] | ((uint32_t)vi[1] << 8) | ((uint32_t)vi[2] << 16) | ((uint32_t)vi[3] << 24);
     }
 }
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(WsCfg<GSW, DC>::NT, WsCfg<GSW, DC>::MINB) k_ag
         const int pw = warp - CW;
         const int f2_start = x0 - dlo - DC + 1 - pad + g.PL2;
         const int c2_start = x0 - dlo - DC + 1 + g.PL2;
-        const size_t e_plane = (size_t)g.UW * EP;
+        const size_t e_plane = GSW ? (size_t)g.UW * EP : (size_t)g.EPL;
         const float4 *C1s = reinterpret_cast<const float4 *>(smem + sp.c1);
         const float4 *C2s = reinterpret_cast<const float4 *>(smem + sp.c2);
 
@@ -1147,7 +1151,7 @@ Plan make_plan(const Call &q) {
     return p;
 }
 
-Geom make_geom(const Call &q, int DC) {
+Geom make_geom(const Call &q, int DC, bool tc) {
     Geom g;
     g.W = q.W; g.H = q.H; g.win = q.win; g.pad = q.win / 2;
     g.minD = q.minD; g.maxD = q.maxD;
@@ -1161,9 +1165,11 @@ Geom make_geom(const Call &q, int DC) {
     g.erow0 = q.row0 - g.pad < 0 ? 0 : q.row0 - g.pad;
     g.erow1 = q.row1 + g.pad > q.H ? q.H : q.row1 + g.pad;
     g.T = q.gsw ? TILE_X : TILE_WS;
-    g.EP = g.DC + 4;
+    g.EP = tc ? TC_EP : g.DC + 4;
+    g.EG = tc ? TC_EG : 0;
     g.ntx = (q.W + g.T - 1) / g.T;
     g.UW = (g.ntx * g.T + g.win - 1 + 3) & ~3;
+    g.EPL = (g.UW * g.EP + ((g.UW + 7) >> 3) * g.EG + 15) & ~15;
     g.PL2 = g.dLo + g.nch * g.DC - 1 + g.pad;
     g.VW = g.ntx * g.T + g.pad + g.PL2;
     g.NU = g.T + g.win - 1;
@@ -1311,12 +1317,12 @@ int run_device(Ctx &c, const Call &q, const uint8_t *d_img1, const uint8_t *d_im
         Call qq = q;
         qq.dBegin = dB;
         qq.dEnd = dE;
-        const Geom g = make_geom(qq, plan.DC);
+        const Geom g = make_geom(qq, plan.DC, plan.tc);
         const int erows = g.erow1 - g.erow0;
         if ((rc = ensure(c.f1, (size_t)erows * g.UW * 16))) return rc;
         if ((rc = ensure(c.f2, (size_t)erows * g.VW * 16))) return rc;
         if ((rc = ensure(c.evol, q.gsw ? (size_t)g.nch * erows * g.UW * g.DC * 4
-                                       : (size_t)g.nch * erows * g.UW * g.EP + 64))) return rc;
+                                       : (size_t)g.nch * erows * g.EPL + 256))) return rc;
         const int Dp = g.nch * g.DC;
         if (o.want_vol0 && (rc = ensure(c.vol0, npx * Dp * 4))) return rc;
         if (o.want_vol1 && (rc = ensure(c.vol1, npx * Dp * 4))) return rc;
