@@ -184,6 +184,24 @@ def test_c2_recovers_ground_truth(c2_pair, c2_full):
     assert (c2_full["final"] >= 0).all()
 
 
+def test_c2_disparity_shift_equivariance(c2_pair, c2_full):
+    """Size-independent property at the full C2 size: with the right image shifted left by k columns and the search range
+    moved up by k (minDisparity = k), every winner moves by exactly k wherever both calls see the same candidates and the same
+    window pixels -- x >= maxD + k + pad (no candidate or window column falls off the left edge in either call) and
+    x <= W - 1 - pad (none reaches the columns the shift had to invent).  Same pairs, same data, other feature / raw-cost
+    offsets (minD > 0 path) at full size: the maps must agree bit for bit."""
+    l, r, _ = c2_pair
+    k, pad, W = 7, C2["winSize"] // 2, l.shape[1]
+    rs = np.empty_like(r)
+    rs[:, :-k] = r[:, k:]
+    rs[:, -k:] = r[:, -1:]
+    kw = dict(C2, minDisparity=k, maxDisparity=C2["maxDisparity"] + k)
+    shifted = ss.passive.StereoASW(consistent=False, **kw).compute_staged(l, rs)["left"]
+    x0, x1 = C2["maxDisparity"] + k + pad, W - pad
+    assert np.array_equal(shifted[:, x0:x1], c2_full["left"][:, x0:x1] + k)
+    parity.record("c2_shift_equivariance", pixels=int(shifted[:, x0:x1].size), shift=k, identical=True)
+
+
 def test_identical_pair_gives_min_disparity():
     """cost(d=minD) is exactly 0 when left == right shifted by minD... here minD = 0: every pixel -> 0."""
     l, _, _ = synth_pair(1242, 64, 127, 4)
