@@ -38,6 +38,11 @@
 #define SS_TC_CREG 136         // registers per consumer / producer thread after setmaxnreg: 12 * CREG + 4 * PREG = 16 * 128
 #define SS_TC_PREG 96
 #endif
+#ifndef SS_TC_S1
+#define SS_TC_S1 5             // left-column batches: producer boundaries in ninths of a column block (see the producers' work split)
+#define SS_TC_S2 11
+#define SS_TC_S3 16
+#endif
 #ifndef SS_TC_PUNROLL
 #define SS_TC_PUNROLL 2        // weight batches (of 4) in flight per producer lane in the right-column loop
 #endif
@@ -117,7 +122,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
     auto BAR = [&](int slot) { return bar0 + 8u * (uint32_t)slot; };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 128);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // The warp index comes out of a shuffle so that ptxas treats it -- and every role branch on it -- as warp-uniform: the
+    // producers' loop control and the whole tcgen05.mma issue loop then run in the uniform datapath (11 instructions per MMA
+    // instead of 19 with an ELECT / 4 x R2UR.BROADCAST / VOTEU group around each; C2 7.87 -> 7.76 ms).  The same change made
+    // the GSW instantiation of k_aggregate_ws 10 % slower and left the ASW one unchanged, so it is applied here only.
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int tile = g.tile0 + (int)blockIdx.x, per_ch = g.ntx * (g.row1 - g.row0);
     const int ch = tile / per_ch, rem = tile - ch * per_ch;
     const int x0 = (rem % g.ntx) * T;
@@ -163,6 +173,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tbase = *tmem_slot;
+    if (tbase != 0u) __trap();   // one block per SM allocates all 512 columns: the only placement is 0 (the issue loop relies on it)
     auto colA = [&](int stage, int half, int lo) {
         return SINGLE ? 192u + (uint32_t)half * 2u * KC + (uint32_t)lo * KC
                       : 192u + (uint32_t)stage * 160u + (uint32_t)half * 80u + (uint32_t)lo * 40u;
@@ -216,9 +227,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
         // full tile: 7 right blocks (producers 0-2 two each, producer 3 one) + 3 left blocks; producer 3 also issues the MMAs and
         // takes 20 of the 90 batches of a 35-wide window (the others 23-24): left shares 5/9, 6/9, 5/9, 11/9 NB
         const int l0 = xsub >= 0 ? xsub * NB + (pw * NB) / 4
-                                 : pw == 0 ? 0 : pw == 1 ? (NB * 5) / 9 : pw == 2 ? (NB * 11) / 9 : (NB * 16) / 9;
+                                 : pw == 0 ? 0 : pw == 1 ? (NB * SS_TC_S1) / 9 : pw == 2 ? (NB * SS_TC_S2) / 9 : (NB * SS_TC_S3) / 9;
         const int l1 = xsub >= 0 ? xsub * NB + ((pw + 1) * NB) / 4
-                                 : pw == 0 ? (NB * 5) / 9 : pw == 1 ? (NB * 11) / 9 : pw == 2 ? (NB * 16) / 9 : 3 * NB;
+                                 : pw == 0 ? (NB * SS_TC_S1) / 9 : pw == 1 ? (NB * SS_TC_S2) / 9 : pw == 2 ? (NB * SS_TC_S3) / 9 : 3 * NB;
         const int l0_blk = l0 / NB, l0_jb = l0 - l0_blk * NB;
         const int o_f1 = sp.f1, o_f2 = sp.f2, o_pa = sp.pa, o_w1 = sp.w1, o_w2 = sp.w2;
         const int b_f1 = sp.f1bytes, b_f2 = sp.f2bytes, b_pa = sp.pabytes, b_w2 = sp.w2bytes, w1arr = sp.w1arr;
@@ -312,21 +323,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
                 mbar_arrive(BAR(3 + st));        // feature stage may be refilled
             }
             // ---- the tensor core: D[r][x] += W2hi*W1hi + W2hi*W1lo + W2lo*W1hi over this window row ----
-            // Producer 3 issues the row's 6 KG MMAs (30 for a 35-wide window): the whole warp runs the loop, the instruction
-            // itself is predicated on elect.sync.  The issue is NOT free: without the MMAs the kernel is 6 % faster (SS_FREERUN=8)
-            // -- about 18 instructions per MMA on a warp that only gets an issue slot every few cycles and whose weights the
-            // whole block waits for.  Tried and rejected: the issue split over two producers (+2 %), issued two at
-            // a time between the next row's weight batches (the bookkeeping costs more than it hides), a 17th warp (see
-            // TC_THREADS).
+            // Producer 3 issues the row's 6 KG MMAs (30 for a 35-wide window).  The whole warp runs the loop (the instruction is
+            // predicated on elect.sync) and, because the role branch is warp-uniform (see `warp`), entirely in the uniform
+            // datapath: 11 instructions per MMA.  The issue is still not free: without the MMAs the kernel is faster
+            // (SS_FREERUN=8) -- issue slots of a warp whose weights the whole block waits for.  Tried and rejected:
+            // the issue split over two producers (+2 %), issued two at a time between the next row's weight batches (the
+            // bookkeeping costs more than it hides), a 17th warp (see TC_THREADS).
             if (pw == 3) {
                 mbar_wait(BAR(5 + sw), phw);     // every producer has arrived: the operands of this row are in place
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const int KGx = (P.freerun & 8) ? 0 : KG;         // timing experiment: no MMAs (the commits still arrive)
-                // (shuffles from lane 0: ptxas then knows these are warp-uniform)
-                const uint32_t bhi = __shfl_sync(0xffffffffu, smem_u32(smem) + (uint32_t)(o_w1 + sw * w1arr), 0);
-                const uint32_t blo = __shfl_sync(0xffffffffu, smem_u32(smem) + (uint32_t)(o_w1 + (2 + (SINGLE ? 0 : sw)) * w1arr), 0);
-                const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0), ca = __shfl_sync(0xffffffffu, colA(sw, 0, 0), 0);
-                const int KGu = __shfl_sync(0xffffffffu, KGx, 0), first = __shfl_sync(0xffffffffu, n == 0 ? 1 : 0, 0);
+                // Every operand of the issue loop is derived from launch parameters, loop counters and constants only (the TMEM base
+                // is 0: the block owns all 512 columns, checked after the allocation), so ptxas can keep them in uniform registers
+                const uint32_t bhi = smem_u32(smem) + (uint32_t)(o_w1 + sw * w1arr);
+                const uint32_t blo = smem_u32(smem) + (uint32_t)(o_w1 + (2 + (SINGLE ? 0 : sw)) * w1arr);
+                const uint32_t tb = 0u, ca = colA(sw, 0, 0);
+                const int KGu = KGx, first = n == 0 ? 1 : 0;
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
 #pragma unroll

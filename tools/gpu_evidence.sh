@@ -22,6 +22,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_ag
 # sanitizers on the small-shape tests (both aggregation kernels, fused L-R epilogue, tail split, multi-chunk)
 SMALL="golden or randomised_small_shapes or multi_chunk or tail_wave or borders or isolated"
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$SMALL" > $O/sanitizer_memcheck.txt 2>&1; tail -3 $O/sanitizer_memcheck.txt
-timeout 900 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "asw_synth_d140 or asw_crop_consistent or gsw_synth or tail_wave" > $O/sanitizer_racecheck.txt 2>&1; tail -3 $O/sanitizer_racecheck.txt
+# racecheck takes 12 minutes under the tool: only with SS_RACECHECK=1
+[ -n "${SS_RACECHECK:-}" ] && timeout 900 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "asw_synth_d140 or asw_crop_consistent or gsw_synth or tail_wave" > $O/sanitizer_racecheck.txt 2>&1; tail -3 $O/sanitizer_racecheck.txt
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $O/smi.csv
 ls -la $O
