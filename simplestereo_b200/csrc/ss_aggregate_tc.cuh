@@ -38,11 +38,6 @@
 #define SS_TC_CREG 136         // registers per consumer / producer thread after setmaxnreg: 12 * CREG + 4 * PREG = 16 * 128
 #define SS_TC_PREG 96
 #endif
-#ifndef SS_TC_S1
-#define SS_TC_S1 5             // left-column batches: producer boundaries in ninths of a column block (see the producers' work split)
-#define SS_TC_S2 11
-#define SS_TC_S3 16
-#endif
 #ifndef SS_TC_PUNROLL
 #define SS_TC_PUNROLL 2        // weight batches (of 4) in flight per producer lane in the right-column loop
 #endif
@@ -227,9 +222,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_aggregate_tc(const AggParams 
         // full tile: 7 right blocks (producers 0-2 two each, producer 3 one) + 3 left blocks; producer 3 also issues the MMAs and
         // takes 20 of the 90 batches of a 35-wide window (the others 23-24): left shares 5/9, 6/9, 5/9, 11/9 NB
         const int l0 = xsub >= 0 ? xsub * NB + (pw * NB) / 4
-                                 : pw == 0 ? 0 : pw == 1 ? (NB * SS_TC_S1) / 9 : pw == 2 ? (NB * SS_TC_S2) / 9 : (NB * SS_TC_S3) / 9;
+                                 : pw == 0 ? 0 : pw == 1 ? (NB * 5) / 9 : pw == 2 ? (NB * 11) / 9 : (NB * 16) / 9;
         const int l1 = xsub >= 0 ? xsub * NB + ((pw + 1) * NB) / 4
-                                 : pw == 0 ? (NB * SS_TC_S1) / 9 : pw == 1 ? (NB * SS_TC_S2) / 9 : pw == 2 ? (NB * SS_TC_S3) / 9 : 3 * NB;
+                                 : pw == 0 ? (NB * 5) / 9 : pw == 1 ? (NB * 11) / 9 : pw == 2 ? (NB * 16) / 9 : 3 * NB;
         const int l0_blk = l0 / NB, l0_jb = l0 - l0_blk * NB;
         const int o_f1 = sp.f1, o_f2 = sp.f2, o_pa = sp.pa, o_w1 = sp.w1, o_w2 = sp.w2;
         const int b_f1 = sp.f1bytes, b_f2 = sp.f2bytes, b_pa = sp.pabytes, b_w2 = sp.w2bytes, w1arr = sp.w1arr;
