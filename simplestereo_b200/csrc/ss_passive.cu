@@ -1432,7 +1432,8 @@ int run_host(Ctx &c, const Call &q, const uint8_t *img1, const uint8_t *img2, in
     if (out_invalid && npx) CU_TRY(cudaMemcpyAsync(out_invalid, o.d_invalid, npx, cudaMemcpyDeviceToHost, st));
     const int D = q.maxD - q.minD + 1;
     if ((out_vol0 || out_vol1) && D > 0 && npx) {
-        const int Dp = ((D + make_plan(q).DC - 1) / make_plan(q).DC) * make_plan(q).DC;
+        const int dc = make_plan(q).DC;
+        const int Dp = ((D + dc - 1) / dc) * dc;
         if ((rc = ensure(c.dense, npx * D * 4))) return rc;
         const long long n = (long long)npx * D;
         for (int v = 0; v < 2; ++v) {
